@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference's operator interface for the learn() hot path.
+
+Same names, argument meaning and error behaviour as lanl-ansi/GraphicalModelLearning.jl:
+  RISE / logRISE / RPLE / multiRISE      src/GraphicalModelLearning.jl:20-56
+  GMLMethod / NLP                        src/GraphicalModelLearning.jl:59-65
+  learn(samples, formulation, method)    src/GraphicalModelLearning.jl:69-73, 83-336
+  data_info                              src/GraphicalModelLearning.jl:76-81
+  FactorGraph (container + conversions)  src/models.jl:8-20, 105-154
+The new method type is `B200` -- the sibling of `NLP` that the Julia shim
+(julia/GMLB200.jl) adds; `learn` dispatches to libgml_b200.so through the C ABI.  There is no
+CPU code path here: `NLP` (JuMP + Ipopt) is not available in this image and raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+# ---- formulations (src/GraphicalModelLearning.jl:20-56) ------------------------------------
+class GMLFormulation:
+    pass
+
+
+@dataclass
+class multiRISE(GMLFormulation):
+    regularizer: float = 0.4
+    symmetrization: bool = True
+    interaction_order: int = 2
+
+
+@dataclass
+class RISE(GMLFormulation):
+    regularizer: float = 0.4
+    symmetrization: bool = True
+
+
+@dataclass
+class RISEA(GMLFormulation):   # dead code in the reference (removed JuMP API), kept for the name only
+    regularizer: float = 0.4
+    symmetrization: bool = True
+
+
+@dataclass
+class logRISE(GMLFormulation):
+    regularizer: float = 0.8
+    symmetrization: bool = True
+
+
+@dataclass
+class RPLE(GMLFormulation):
+    regularizer: float = 0.2
+    symmetrization: bool = True
+
+
+# ---- methods (src/GraphicalModelLearning.jl:59-65) -----------------------------------------
+class GMLMethod:
+    pass
+
+
+@dataclass
+class NLP(GMLMethod):
+    solver: object = None
+
+
+@dataclass
+class B200(GMLMethod):
+    """Batched GPU solver.  tol: stopping tolerance (prox-gradient mapping max-norm for FISTA,
+    Newton step for the small-problem solver; 0 = solver default 1e-6 / 1e-12).  barrier_mu > 0
+    returns the log-barrier point Ipopt stops at (use 1e-9 to reproduce the reference's stored
+    fixtures to ~1e-9) instead of the exact L1 minimiser."""
+    tol: float = 0.0
+    max_iter: int = 0
+    solver: str = "auto"          # auto | newton | fista_cc | fista_tc
+    barrier_mu: float = 0.0
+    device: int = 0
+    verbose: int = 0
+    last_stats: dict = field(default_factory=dict, repr=False, compare=False)
+
+    def _opts(self, node_begin: int = 0, node_end: int = 0, stream: int = 0) -> _lib.Opts:
+        o = _lib.default_opts()
+        o.tol = float(self.tol)
+        o.max_iter = int(self.max_iter)
+        o.solver = {"auto": 0, "newton": 1, "fista_cc": 2, "fista_tc": 3}[self.solver]
+        o.barrier_mu = float(self.barrier_mu)
+        o.device = int(self.device)
+        o.verbose = int(self.verbose)
+        o.node_begin, o.node_end = int(node_begin), int(node_end)
+        o.stream = ctypes.c_void_p(stream) if stream else None
+        return o
+
+
+# ---- FactorGraph (src/models.jl) ------------------------------------------------------------
+@dataclass
+class FactorGraph:
+    order: int
+    varible_count: int            # sic -- the reference's spelling (src/models.jl:10)
+    alphabet: str
+    terms: Dict[Tuple[int, ...], float]
+    variable_names: Optional[list] = None
+
+    def __getitem__(self, key):
+        return self.terms[tuple(key)]
+
+    def __iter__(self):
+        return iter(self.terms.items())
+
+    def keys(self):
+        return self.terms.keys()
+
+    @staticmethod
+    def from_matrix(m) -> "FactorGraph":
+        """FactorGraph(matrix): diagonal -> (i,), upper triangle -> (i,j); zeros dropped
+        (src/models.jl:105-135).  Keys are 1-based like the reference's."""
+        m = np.asarray(m, dtype=np.float64)
+        assert m.shape[0] == m.shape[1]
+        n = m.shape[0]
+        terms = {}
+        for i in range(n):
+            if not math.isclose(m[i, i], 0.0, abs_tol=0.0):
+                terms[(i + 1,)] = float(m[i, i])
+        for i in range(n):
+            for j in range(i + 1, n):
+                if not math.isclose(m[i, j], 0.0, abs_tol=0.0):
+                    terms[(i + 1, j + 1)] = float(m[i, j])
+        return FactorGraph(2, n, "spin", terms)
+
+    def to_matrix(self) -> np.ndarray:
+        """convert(Array{T,2}, gm) (src/models.jl:137-154)."""
+        if self.order != 2:
+            raise ValueError(f"cannot convert a FactorGraph of order {self.order} to a matrix")
+        m = np.zeros((self.varible_count, self.varible_count))
+        for k, v in self.terms.items():
+            if len(k) == 1:
+                m[k[0] - 1, k[0] - 1] = v
+            else:
+                m[k[0] - 1, k[1] - 1] = v
+                m[k[1] - 1, k[0] - 1] = v
+        return m
+
+
+def matrix_to_dict(m) -> Dict[Tuple[int, ...], float]:
+    """convert(Dict, matrix): all ordered pairs + diagonal (src/models.jl:157-182)."""
+    m = np.asarray(m)
+    n = m.shape[0]
+    out = {}
+    for i in range(n):
+        if m[i, i] != 0.0:
+            out[(i + 1,)] = float(m[i, i])
+    for i in range(n):
+        for j in range(n):
+            if i != j and m[i, j] != 0.0:
+                out[(i + 1, j + 1)] = float(m[i, j])
+    return out
+
+
+# ---- learn ------------------------------------------------------------------------------------
+def data_info(samples):
+    """(num_conf, num_spins, num_samples) -- src/GraphicalModelLearning.jl:76-81."""
+    num_conf, num_row = samples.shape
+    return num_conf, num_row - 1, samples[:, 0].sum()
+
+
+def regularizer_lambda(c: float, num_spins: int, num_samples: float) -> float:
+    """src/GraphicalModelLearning.jl:157."""
+    return c * math.sqrt(math.log((num_spins ** 2) / 0.05) / num_samples)
+
+
+def pack_histogram(samples):
+    """[count, s_1..s_N] (any real dtype, any memory order -- the Adjoint shim of :73 is a no-op
+    here) -> counts float64[K], spins int8 spin-major [N x K]."""
+    samples = np.asarray(samples)
+    if samples.ndim != 2 or samples.shape[1] < 2 or samples.shape[0] < 1:
+        raise ValueError("samples must be a K x (N+1) matrix [count, s_1..s_N]")
+    counts = np.ascontiguousarray(samples[:, 0], dtype=np.float64)
+    body = samples[:, 1:]
+    spins = np.ascontiguousarray(body.T.astype(np.int8))
+    if not np.array_equal(spins, body.T):
+        raise ValueError("spin columns must be exactly -1 or +1")
+    return counts, spins
+
+
+def multirise_keys(num_spins: int, u: int, inter_order: int):
+    """Keys of node u in the reference's order (src/GraphicalModelLearning.jl:94-104 with
+    permutations() of src/models.jl:228-246 = ascending combinations), 1-based."""
+    import itertools
+    neighbours = [i for i in range(1, num_spins + 1) if i != u]
+    keys = [(u,)]
+    for p in range(2, inter_order + 1):
+        keys.extend((u,) + c for c in itertools.combinations(neighbours, p - 1))
+    return keys
+
+
+def _ptr(a: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def learn_packed(counts: np.ndarray, spins: np.ndarray, formulation: GMLFormulation, method: B200,
+                 lam: Optional[float] = None, return_info: bool = False):
+    """learn() on a pre-packed histogram (counts f64[K], spins int8 [N x K] spin-major)."""
+    lib = _lib.load()
+    N, K = spins.shape
+    assert counts.dtype == np.float64 and spins.dtype == np.int8 and counts.shape == (K,)
+    assert spins.strides[1] == 1
+    ld = spins.strides[0]
+    if lam is None:
+        lam = regularizer_lambda(formulation.regularizer, N, float(counts.sum()))
+    stats = _lib.Stats()
+    obj = np.zeros(N)
+    opts = method._opts()
+    if isinstance(formulation, multiRISE):
+        order = int(formulation.interaction_order)
+        n_keys = int(lib.gml_b200_multibody_num_keys(N, order))
+        vals = np.zeros((N, n_keys))
+        rc = lib.gml_b200_learn_multibody(_ptr(counts), _ptr(spins), K, N, ld, order, lam,
+                                          ctypes.byref(opts), _ptr(vals), _ptr(obj), ctypes.byref(stats))
+        method.last_stats = stats.as_dict()
+        _lib.check(rc)
+        recon = {}
+        for u in range(1, N + 1):
+            for f, key in enumerate(multirise_keys(N, u, order)):
+                recon[key] = float(vals[u - 1, f])                      # :129-132
+        if formulation.symmetrization:                                   # :135-149
+            groups: Dict[Tuple[int, ...], list] = {}
+            for k, v in recon.items():
+                groups.setdefault(tuple(sorted(k)), []).append(v)
+            recon = {k: float(np.mean(v)) for k, v in groups.items()}
+        result = FactorGraph(order, N, "spin", recon)                    # :151
+    else:
+        form_id = {RISE: 0, logRISE: 1, RPLE: 2}.get(type(formulation))
+        if form_id is None:
+            raise NotImplementedError(f"{type(formulation).__name__} is not on the B200 hot path")
+        theta = np.zeros((N, N), order="F")                              # Julia-native column-major
+        rc = lib.gml_b200_learn_pairwise(_ptr(counts), _ptr(spins), K, N, ld, form_id, lam,
+                                         int(bool(formulation.symmetrization)), ctypes.byref(opts),
+                                         _ptr(theta), _ptr(obj), ctypes.byref(stats))
+        method.last_stats = stats.as_dict()
+        _lib.check(rc)
+        result = np.ascontiguousarray(theta)
+    if return_info:
+        return result, {"lambda": lam, "objective": obj, **method.last_stats}
+    return result
+
+
+def learn(samples, formulation: Optional[GMLFormulation] = None, method: Optional[GMLMethod] = None,
+          return_info: bool = False):
+    """learn(samples[, formulation[, method]]) -- src/GraphicalModelLearning.jl:69-73.
+    Pairwise formulations return the N x N matrix (row u = node u, diagonal = fields, :181-188);
+    multiRISE returns a FactorGraph (:151).  Raises on solver failure like the reference's
+    @assert (:180)."""
+    formulation = RISE() if formulation is None else formulation
+    method = B200() if method is None else method
+    if isinstance(method, NLP):
+        raise NotImplementedError("NLP (JuMP + Ipopt) is the reference's CPU method and is not available here; "
+                                  "pass B200() as the method")
+    if not isinstance(method, B200):
+        raise TypeError("method must be a GMLMethod")
+    counts, spins = pack_histogram(samples)
+    return learn_packed(counts, spins, formulation, method, return_info=return_info)

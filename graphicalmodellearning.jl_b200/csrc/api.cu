@@ -1,0 +1,520 @@
+// C ABI of libgml_b200 (see include/gml_b200.h): handle management, problem set-up, solver dispatch,
+// row placement / symmetrisation (src/GraphicalModelLearning.jl:181-186) and result transfer.
+#include "common.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+
+namespace gml {
+
+thread_local std::string g_error;
+thread_local int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_error = msg; }
+
+namespace {
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st;
+    explicit EventTimer(cudaStream_t s) : st(s) {
+        GML_CUDA(cudaEventCreate(&a)); GML_CUDA(cudaEventCreate(&b));
+        GML_CUDA(cudaEventRecord(a, st));
+    }
+    double stop() {
+        float ms = 0.f;
+        GML_CUDA(cudaEventRecord(b, st));
+        GML_CUDA(cudaEventSynchronize(b));
+        GML_CUDA(cudaEventElapsedTime(&ms, a, b));
+        return ms;
+    }
+    ~EventTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
+// pairwise penalty classes (:171): coupling to itself does not exist, the field is free
+__global__ void pairwise_setup_kernel(int N, int Fp, int node_begin, int Nn, int32_t* spin_row, uint8_t* pen) {
+    const int u = blockIdx.x;
+    if (threadIdx.x == 0) spin_row[u] = node_begin + u;
+    for (int f = threadIdx.x; f < Fp; f += blockDim.x) {
+        uint8_t c = PEN_ZERO;
+        if (f < N) c = (f == node_begin + u) ? PEN_ZERO : PEN_L1;
+        else if (f == N) c = PEN_FREE;
+        pen[(int64_t)u * Fp + f] = c;
+    }
+}
+
+// reconstruction[u, 1:N] = value.(x) (:181): coupling columns, field on the diagonal
+__global__ void pairwise_rows_kernel(const double* __restrict__ x, int N, int Fp, int node_begin, double* __restrict__ rows) {
+    const int u = blockIdx.x;
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        rows[(int64_t)u * N + i] = (i == node_begin + u) ? x[(int64_t)u * Fp + N] : x[(int64_t)u * Fp + i];
+}
+
+__global__ void symmetrize_kernel(double* __restrict__ m, int N) {
+    const int i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && j < N && j > i) {
+        const double v = 0.5 * (m[(int64_t)i * N + j] + m[(int64_t)j * N + i]);   // 0.5*(R + R') (:185)
+        m[(int64_t)i * N + j] = v; m[(int64_t)j * N + i] = v;
+    }
+}
+
+__global__ void multibody_setup_kernel(int Fp, int n_keys, const int32_t* __restrict__ key_map, int32_t* spin_row, uint8_t* pen) {
+    const int u = blockIdx.x;
+    if (threadIdx.x == 0) spin_row[u] = u;
+    for (int f = threadIdx.x; f < Fp; f += blockDim.x) pen[(int64_t)u * Fp + f] = PEN_ZERO;
+    __syncthreads();
+    for (int f = threadIdx.x; f < n_keys; f += blockDim.x)
+        pen[(int64_t)u * Fp + key_map[(int64_t)u * n_keys + f]] = (f == 0) ? PEN_FREE : PEN_L1;   // length-1 key is free (:118)
+}
+
+__global__ void multibody_gather_kernel(const double* __restrict__ x, int Fp, int n_keys, const int32_t* __restrict__ key_map,
+                                        double* __restrict__ vals) {
+    const int u = blockIdx.x;
+    for (int f = threadIdx.x; f < n_keys; f += blockDim.x)
+        vals[(int64_t)u * n_keys + f] = x[(int64_t)u * Fp + key_map[(int64_t)u * n_keys + f]];
+}
+
+int64_t binom(int n, int k) {
+    if (k < 0 || k > n) return 0;
+    long double r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+    return (int64_t)llround((double)r);
+}
+
+void fill_opts(gml_b200_opts& o, const gml_b200_opts* in) {
+    gml_b200_opts_default(&o);
+    if (in) o = *in;
+}
+
+int pick_solver(const gml_b200_opts& o, int F) {
+    int s = o.solver;
+    if (s == GML_B200_SOLVER_AUTO) s = (F <= NEWTON_MAX_F) ? GML_B200_SOLVER_NEWTON : GML_B200_SOLVER_FISTA_TC;
+    GML_REQUIRE(s >= GML_B200_SOLVER_NEWTON && s <= GML_B200_SOLVER_FISTA_TC, "unknown solver id");
+    GML_REQUIRE(s != GML_B200_SOLVER_NEWTON || F <= NEWTON_MAX_F, "Newton solver needs <= 64 features per node");
+    GML_REQUIRE(o.barrier_mu == 0.0 || s == GML_B200_SOLVER_NEWTON,
+                "barrier_mu (Ipopt-compatible mode) is only available with the Newton solver (<= 64 features)");
+    return s;
+}
+
+void run_solver(const NodeProblem& p, const gml_b200_opts& o, SolveResult& r, int& solver_used, cudaStream_t st) {
+    solver_used = pick_solver(o, p.F);
+    if (solver_used == GML_B200_SOLVER_NEWTON) solve_newton(p, o, r, st);
+    else solve_fista(p, o, solver_used, r, st);
+}
+
+}  // namespace
+}  // namespace gml
+
+using namespace gml;
+
+struct gml_b200_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    Histogram hist;
+    bool has_hist = false;
+};
+
+namespace {
+
+cudaStream_t stream_of(gml_b200_handle* h, const gml_b200_opts& o) {
+    return o.stream ? (cudaStream_t)o.stream : h->own_stream;
+}
+
+template <class Fn> int guarded(Fn&& fn) {
+    try {
+        fn();
+        return GML_B200_OK;
+    } catch (const CudaError& e) {
+        return e.code;
+    } catch (const std::exception& e) {
+        set_error(std::string("internal error: ") + e.what());
+        return GML_B200_ECUDA;
+    }
+}
+
+void finish_stats(gml_b200_stats* stats, const SolveResult& r, int solver_used, int Nn, int64_t K, double solve_ms,
+                  double d2h_ms, double t0) {
+    if (!stats) return;
+    stats->solver_used = solver_used;
+    stats->iterations = r.iterations;
+    stats->n_fg_passes = r.n_fg;
+    stats->n_f_passes = r.n_f;
+    stats->n_unconverged = r.n_unconverged;
+    stats->kernel_launches = g_launches;
+    stats->evals = (double)Nn * (double)K * (r.n_fg + 0.5 * r.n_f);
+    stats->solve_ms = solve_ms;
+    stats->d2h_ms = d2h_ms;
+    stats->total_ms += now_ms() - t0;
+    stats->max_residual = r.max_residual;
+}
+
+void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, const gml_b200_opts& o, int nb, int ne,
+                         double* d_rows, double* d_obj, gml_b200_stats* stats, cudaStream_t st, double t0) {
+    GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
+    GML_REQUIRE(formulation >= GML_B200_RISE && formulation <= GML_B200_RPLE, "unknown formulation id");
+    GML_REQUIRE(lambda >= 0.0 && std::isfinite(lambda), "lambda must be finite and >= 0");
+    Histogram& hist = h->hist;
+    const int N = hist.N;
+    GML_REQUIRE(nb >= 0 && ne <= N && nb < ne, "node shard out of range");
+    NodeProblem p;
+    p.hist = &hist; p.Q = hist.base.p; p.F = N + 1; p.Fp = hist.Fb;
+    p.form = formulation; p.lambda = lambda; p.Nn = ne - nb;
+    p.spin_row.alloc(p.Nn); p.pen.alloc((size_t)p.Nn * p.Fp);
+    EventTimer timer(st);
+    pairwise_setup_kernel<<<p.Nn, 128, 0, st>>>(N, p.Fp, nb, p.Nn, p.spin_row.p, p.pen.p);
+    GML_LAUNCHED();
+    SolveResult r;
+    int solver_used = 0;
+    run_solver(p, o, r, solver_used, st);
+    pairwise_rows_kernel<<<p.Nn, 128, 0, st>>>(r.x.p, N, p.Fp, nb, d_rows);
+    GML_LAUNCHED();
+    if (d_obj) GML_CUDA(cudaMemcpyAsync(d_obj, r.objective.p, sizeof(double) * p.Nn, cudaMemcpyDeviceToDevice, st));
+    const double solve_ms = timer.stop();
+    finish_stats(stats, r, solver_used, p.Nn, hist.K, solve_ms, 0.0, t0);
+    if (r.n_unconverged > 0) {
+        set_error("solver did not reach tol within max_iter for " + std::to_string(r.n_unconverged) + " node(s)");
+        throw CudaError{GML_B200_ENOTCONV};
+    }
+}
+
+// base features of multiRISE order p: all subsets of [N] of size <= p-1, by size then lexicographic
+struct MultibodyLayout {
+    int F = 0, n_keys = 0, width = 0;
+    std::vector<int32_t> subsets;   // [F x width]
+    std::vector<int32_t> key_map;   // [N x n_keys] base-feature index of node u's f-th key
+};
+
+MultibodyLayout multibody_layout(int N, int order) {
+    MultibodyLayout L;
+    L.width = std::max(1, order - 1);
+    std::map<std::vector<int>, int> index;
+    std::vector<std::vector<int>> all;
+    for (int q = 0; q <= order - 1 && q <= N; ++q) {
+        std::vector<int> c(q);
+        for (int i = 0; i < q; ++i) c[i] = i;
+        for (;;) {
+            index[c] = (int)all.size();
+            all.push_back(c);
+            int i = q - 1;
+            while (i >= 0 && c[i] == N - q + i) --i;
+            if (i < 0) break;
+            ++c[i];
+            for (int j = i + 1; j < q; ++j) c[j] = c[j - 1] + 1;
+        }
+    }
+    L.F = (int)all.size();
+    L.subsets.assign((size_t)L.F * L.width, -1);
+    for (int f = 0; f < L.F; ++f)
+        for (size_t j = 0; j < all[f].size(); ++j) L.subsets[(size_t)f * L.width + j] = all[f][j];
+    // node keys in the reference's order (:94-104): (u,), (u, comb of neighbours of size 1), size 2, ...
+    for (int u = 0; u < N; ++u) {
+        int count = 0;
+        for (int q = 0; q <= order - 1 && q <= N - 1; ++q) {
+            std::vector<int> c(q);   // combination over the N-1 neighbours, mapped to spin ids
+            for (int i = 0; i < q; ++i) c[i] = i;
+            for (;;) {
+                std::vector<int> ids(q);
+                for (int i = 0; i < q; ++i) ids[i] = c[i] < u ? c[i] : c[i] + 1;
+                L.key_map.push_back(index[ids]);
+                ++count;
+                int i = q - 1;
+                while (i >= 0 && c[i] == (N - 1) - q + i) --i;
+                if (i < 0) break;
+                ++c[i];
+                for (int j = i + 1; j < q; ++j) c[j] = c[j - 1] + 1;
+            }
+        }
+        L.n_keys = count;
+    }
+    return L;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gml_b200_version(void) { return "gml_b200 0.1.0 (sm_100a)"; }
+const char* gml_b200_last_error(void) { return g_error.c_str(); }
+
+int gml_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void gml_b200_opts_default(gml_b200_opts* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->tol = 0.0;           // 0 = solver default (1e-6 FISTA, 1e-12 Newton)
+    o->barrier_mu = 0.0;
+    o->max_iter = 0;        // 0 = solver default
+    o->solver = GML_B200_SOLVER_AUTO;
+    o->device = 0;
+    o->node_begin = 0; o->node_end = 0;
+}
+
+int64_t gml_b200_multibody_num_keys(int32_t N, int32_t order) {
+    int64_t n = 0;
+    for (int q = 0; q <= order - 1; ++q) n += binom(N - 1, q);
+    return n;
+}
+
+int gml_b200_create(gml_b200_handle** out, int32_t device) {
+    return guarded([&] {
+        GML_REQUIRE(out != nullptr, "null handle pointer");
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+            cudaGetLastError();
+            set_error("no CUDA device available: libgml_b200 has no CPU fallback");
+            throw CudaError{GML_B200_ECUDA};
+        }
+        GML_REQUIRE(device >= 0 && device < n, "device ordinal out of range");
+        GML_CUDA(cudaSetDevice(device));
+        auto* h = new gml_b200_handle();
+        h->device = device;
+        GML_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        *out = h;
+    });
+}
+
+void gml_b200_destroy(gml_b200_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+double gml_b200_num_samples(const gml_b200_handle* h) { return h ? h->hist.M : 0.0; }
+
+int gml_b200_attach_histogram_device(gml_b200_handle* h, const double* d_counts, const int8_t* d_spins, int64_t K,
+                                     int32_t N, int64_t ld, gml_b200_stats* stats) {
+    return guarded([&] {
+        GML_REQUIRE(h && d_counts && d_spins, "null argument");
+        const double t0 = now_ms();
+        g_launches = 0;
+        GML_CUDA(cudaSetDevice(h->device));
+        cudaStream_t st = h->own_stream;
+        EventTimer timer(st);
+        h->has_hist = false;
+        hist_from_device(h->hist, d_counts, d_spins, K, N, ld, st);
+        h->has_hist = true;
+        if (stats) {
+            std::memset(stats, 0, sizeof(*stats));
+            stats->pack_ms = timer.stop();
+            stats->kernel_launches = g_launches;
+            stats->total_ms = now_ms() - t0;
+        }
+    });
+}
+
+int gml_b200_upload_histogram(gml_b200_handle* h, const double* counts, const int8_t* spins, int64_t K, int32_t N,
+                              int64_t ld, gml_b200_stats* stats) {
+    return guarded([&] {
+        GML_REQUIRE(h && counts && spins, "null argument");
+        GML_REQUIRE(K >= 1 && N >= 1 && ld >= K, "histogram needs K >= 1, N >= 1, ld >= K");
+        const double t0 = now_ms();
+        GML_CUDA(cudaSetDevice(h->device));
+        cudaStream_t st = h->own_stream;
+        DevBuf<double> dc;
+        DevBuf<int8_t> ds;
+        dc.alloc(K);
+        ds.alloc((size_t)N * K);
+        EventTimer timer(st);
+        GML_CUDA(cudaMemcpyAsync(dc.p, counts, sizeof(double) * K, cudaMemcpyHostToDevice, st));
+        GML_CUDA(cudaMemcpy2DAsync(ds.p, K, spins, ld, K, N, cudaMemcpyHostToDevice, st));
+        const double h2d = timer.stop();
+        gml_b200_stats tmp;
+        const int rc = gml_b200_attach_histogram_device(h, dc.p, ds.p, K, N, K, &tmp);
+        if (rc != GML_B200_OK) throw CudaError{rc};
+        if (stats) {
+            *stats = tmp;
+            stats->h2d_ms = h2d;
+            stats->total_ms = now_ms() - t0;
+        }
+    });
+}
+
+int gml_b200_solve_pairwise_device(gml_b200_handle* h, int32_t formulation, double lambda, const gml_b200_opts* opts,
+                                   double* d_out_rows, double* d_out_objective, gml_b200_stats* stats) {
+    return guarded([&] {
+        GML_REQUIRE(h && d_out_rows, "null argument");
+        const double t0 = now_ms();
+        g_launches = 0;
+        gml_b200_opts o; fill_opts(o, opts);
+        GML_CUDA(cudaSetDevice(h->device));
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        const int nb = o.node_begin, ne = o.node_end > 0 ? o.node_end : h->hist.N;
+        solve_pairwise_rows(h, formulation, lambda, o, nb, ne, d_out_rows, d_out_objective, stats, stream_of(h, o), t0);
+    });
+}
+
+int gml_b200_solve_pairwise(gml_b200_handle* h, int32_t formulation, double lambda, int32_t symmetrize,
+                            const gml_b200_opts* opts, double* out_theta, double* out_objective, gml_b200_stats* stats) {
+    return guarded([&] {
+        GML_REQUIRE(h && out_theta, "null argument");
+        GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
+        const double t0 = now_ms();
+        g_launches = 0;
+        gml_b200_opts o; fill_opts(o, opts);
+        GML_CUDA(cudaSetDevice(h->device));
+        cudaStream_t st = stream_of(h, o);
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        const int N = h->hist.N;
+        const int nb = o.node_begin, ne = o.node_end > 0 ? o.node_end : N;
+        GML_REQUIRE(nb >= 0 && ne <= N && nb < ne, "node shard out of range");
+        const int Nn = ne - nb;
+        DevBuf<double> rows, obj;
+        rows.alloc((size_t)Nn * N); obj.alloc(Nn);
+        int rc = GML_B200_OK;
+        try {
+            solve_pairwise_rows(h, formulation, lambda, o, nb, ne, rows.p, obj.p, stats, st, t0);
+        } catch (const CudaError& e) {
+            if (e.code != GML_B200_ENOTCONV) throw;
+            rc = e.code;   // still hand back the best iterate, then report
+        }
+        EventTimer timer(st);
+        if (symmetrize && Nn == N) {
+            dim3 b(32, 8), g((unsigned)ceil_div(N, 32), (unsigned)ceil_div(N, 8));
+            symmetrize_kernel<<<g, b, 0, st>>>(rows.p, N);
+            GML_LAUNCHED();
+        }
+        std::vector<double> hrows((size_t)Nn * N);
+        GML_CUDA(cudaMemcpyAsync(hrows.data(), rows.p, sizeof(double) * Nn * N, cudaMemcpyDeviceToHost, st));
+        if (out_objective) GML_CUDA(cudaMemcpyAsync(out_objective + nb, obj.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost, st));
+        const double d2h = timer.stop();
+        for (int u = 0; u < Nn; ++u)
+            for (int i = 0; i < N; ++i) out_theta[(size_t)(nb + u) + (size_t)N * i] = hrows[(size_t)u * N + i];
+        if (stats) { stats->d2h_ms = d2h; stats->kernel_launches = g_launches; stats->total_ms = now_ms() - t0; }
+        if (rc != GML_B200_OK) throw CudaError{rc};
+    });
+}
+
+int gml_b200_solve_multibody(gml_b200_handle* h, int32_t order, double lambda, const gml_b200_opts* opts,
+                             double* out_vals, double* out_objective, gml_b200_stats* stats) {
+    return guarded([&] {
+        GML_REQUIRE(h && out_vals, "null argument");
+        GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
+        GML_REQUIRE(order >= 1, "interaction_order must be >= 1");
+        GML_REQUIRE(lambda >= 0.0 && std::isfinite(lambda), "lambda must be finite and >= 0");
+        const double t0 = now_ms();
+        g_launches = 0;
+        gml_b200_opts o; fill_opts(o, opts);
+        GML_CUDA(cudaSetDevice(h->device));
+        cudaStream_t st = stream_of(h, o);
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        Histogram& hist = h->hist;
+        const int N = hist.N;
+        int64_t nf = 0;
+        for (int q = 0; q <= order - 1; ++q) nf += binom(N, q);
+        GML_REQUIRE(nf <= (1 << 16), "multiRISE feature count exceeds 65536: reduce interaction_order");
+        MultibodyLayout L = multibody_layout(N, order);
+        EventTimer timer(st);
+        build_multibody_features(hist, order, L.subsets, L.F, st);
+        NodeProblem p;
+        p.hist = &hist; p.Q = hist.mb.p; p.F = L.F; p.Fp = hist.mb_Fp;
+        p.form = GML_B200_RISE; p.lambda = lambda; p.Nn = N;
+        p.spin_row.alloc(N); p.pen.alloc((size_t)N * p.Fp);
+        DevBuf<int32_t> key_map;
+        key_map.alloc(L.key_map.size());
+        GML_CUDA(cudaMemcpyAsync(key_map.p, L.key_map.data(), sizeof(int32_t) * L.key_map.size(), cudaMemcpyHostToDevice, st));
+        multibody_setup_kernel<<<N, 128, 0, st>>>(p.Fp, L.n_keys, key_map.p, p.spin_row.p, p.pen.p);
+        GML_LAUNCHED();
+        SolveResult r;
+        int solver_used = 0;
+        run_solver(p, o, r, solver_used, st);
+        DevBuf<double> vals;
+        vals.alloc((size_t)N * L.n_keys);
+        multibody_gather_kernel<<<N, 128, 0, st>>>(r.x.p, p.Fp, L.n_keys, key_map.p, vals.p);
+        GML_LAUNCHED();
+        const double solve_ms = timer.stop();
+        EventTimer t2(st);
+        GML_CUDA(cudaMemcpyAsync(out_vals, vals.p, sizeof(double) * N * L.n_keys, cudaMemcpyDeviceToHost, st));
+        if (out_objective) GML_CUDA(cudaMemcpyAsync(out_objective, r.objective.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+        const double d2h = t2.stop();
+        finish_stats(stats, r, solver_used, N, hist.K, solve_ms, d2h, t0);
+        if (r.n_unconverged > 0) {
+            set_error("solver did not reach tol within max_iter for " + std::to_string(r.n_unconverged) + " node(s)");
+            throw CudaError{GML_B200_ENOTCONV};
+        }
+    });
+}
+
+int gml_b200_symmetrize_device(double* d_theta, int32_t N, void* stream) {
+    return guarded([&] {
+        GML_REQUIRE(d_theta && N >= 1, "bad argument");
+        dim3 b(32, 8), g((unsigned)ceil_div(N, 32), (unsigned)ceil_div(N, 8));
+        symmetrize_kernel<<<g, b, 0, (cudaStream_t)stream>>>(d_theta, N);
+        GML_LAUNCHED();
+    });
+}
+
+int gml_b200_learn_pairwise(const double* counts, const int8_t* spins, int64_t K, int32_t N, int64_t ld,
+                            int32_t formulation, double lambda, int32_t symmetrize, const gml_b200_opts* opts,
+                            double* out_theta, double* out_objective, gml_b200_stats* stats) {
+    gml_b200_handle* h = nullptr;
+    int rc = gml_b200_create(&h, opts ? opts->device : 0);
+    if (rc != GML_B200_OK) return rc;
+    gml_b200_stats up{}, so{};
+    rc = gml_b200_upload_histogram(h, counts, spins, K, N, ld, &up);
+    if (rc == GML_B200_OK) rc = gml_b200_solve_pairwise(h, formulation, lambda, symmetrize, opts, out_theta, out_objective, &so);
+    if (stats) {
+        *stats = so;
+        stats->pack_ms = up.pack_ms; stats->h2d_ms = up.h2d_ms;
+        stats->kernel_launches += up.kernel_launches;
+        stats->total_ms += up.total_ms;
+    }
+    gml_b200_destroy(h);
+    return rc;
+}
+
+int gml_b200_learn_multibody(const double* counts, const int8_t* spins, int64_t K, int32_t N, int64_t ld,
+                             int32_t order, double lambda, const gml_b200_opts* opts, double* out_vals,
+                             double* out_objective, gml_b200_stats* stats) {
+    gml_b200_handle* h = nullptr;
+    int rc = gml_b200_create(&h, opts ? opts->device : 0);
+    if (rc != GML_B200_OK) return rc;
+    gml_b200_stats up{}, so{};
+    rc = gml_b200_upload_histogram(h, counts, spins, K, N, ld, &up);
+    if (rc == GML_B200_OK) rc = gml_b200_solve_multibody(h, order, lambda, opts, out_vals, out_objective, &so);
+    if (stats) {
+        *stats = so;
+        stats->pack_ms = up.pack_ms; stats->h2d_ms = up.h2d_ms;
+        stats->kernel_launches += up.kernel_launches;
+        stats->total_ms += up.total_ms;
+    }
+    gml_b200_destroy(h);
+    return rc;
+}
+
+int gml_b200_sample_gibbs_device(int32_t device, int32_t N, const int32_t* row_ptr, const int32_t* col_idx,
+                                 const float* coupling, const float* field, int64_t n_samples, int32_t sweeps,
+                                 uint64_t seed, int8_t* d_spins, int64_t ld, void* stream) {
+    return guarded([&] {
+        GML_REQUIRE(N >= 1 && N <= 4096 && row_ptr && col_idx && coupling && d_spins, "bad sampler argument");
+        GML_REQUIRE(n_samples >= 1 && ld >= n_samples && sweeps >= 1, "bad sampler sizes");
+        GML_CUDA(cudaSetDevice(device));
+        cudaStream_t st = (cudaStream_t)stream;
+        const int nnz = row_ptr[N];
+        int max_deg = 0;
+        for (int i = 0; i < N; ++i) max_deg = std::max(max_deg, row_ptr[i + 1] - row_ptr[i]);
+        DevBuf<int32_t> rp, ci;
+        DevBuf<float> jj, hh;
+        rp.alloc(N + 1); ci.alloc(std::max(nnz, 1)); jj.alloc(std::max(nnz, 1)); hh.alloc(N);
+        std::vector<float> hz(N, 0.f);
+        GML_CUDA(cudaMemcpyAsync(rp.p, row_ptr, sizeof(int32_t) * (N + 1), cudaMemcpyHostToDevice, st));
+        GML_CUDA(cudaMemcpyAsync(ci.p, col_idx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, st));
+        GML_CUDA(cudaMemcpyAsync(jj.p, coupling, sizeof(float) * nnz, cudaMemcpyHostToDevice, st));
+        GML_CUDA(cudaMemcpyAsync(hh.p, field ? field : hz.data(), sizeof(float) * N, cudaMemcpyHostToDevice, st));
+        sample_gibbs(N, rp.p, ci.p, jj.p, hh.p, max_deg, n_samples, sweeps, seed, d_spins, ld, st);
+        GML_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// Shared declarations of libgml_b200: device problem description, error plumbing, launch counting.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/gml_b200.h"
+
+namespace gml {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (no exceptions across the C ABI: everything funnels into a thread-local string)
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+struct CudaError { int code; };
+
+#define GML_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::gml::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) +       \
+                             " (" __FILE__ ":" + std::to_string(__LINE__) + ")");              \
+            throw ::gml::CudaError{GML_B200_ECUDA};                                            \
+        }                                                                                      \
+    } while (0)
+
+#define GML_REQUIRE(cond, msg)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            ::gml::set_error(std::string(msg));                                                \
+            throw ::gml::CudaError{GML_B200_EINVAL};                                           \
+        }                                                                                      \
+    } while (0)
+
+extern thread_local int64_t g_launches;   // kernels launched by the current call
+#define GML_LAUNCHED()                                                                         \
+    do { ++::gml::g_launches; GML_CUDA(cudaGetLastError()); } while (0)
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        if (count <= n && p) return;
+        release();
+        GML_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// penalty classes of a (node, feature) coordinate
+enum : uint8_t { PEN_FREE = 0, PEN_L1 = 1, PEN_ZERO = 2 };
+
+constexpr int KPAD = 128;   // sample padding (rows of the histogram)
+constexpr int FPAD = 128;   // feature padding
+
+// ---------------------------------------------------------------------------------------------
+// Resident histogram.
+//   base  : int8 [Fb x Kp], feature-major (sample-contiguous), Fb = round_up(N+1, FPAD).
+//           Row i < N is spin i (the reference's samples[:,1+i]), row N is the constant 1 (its
+//           coefficient is the local field), rows > N are 0.  Padded samples (k >= K) hold +1 and
+//           carry weight 0.  This is the pairwise feature matrix [S | 1] itself.
+//   mb    : int8 [mb_Fp x Kp] multibody base-feature matrix (products of spins), built on demand.
+//   P     : int8 [Kp x Fp] sample-major (feature-contiguous) copy of the active feature matrix,
+//           built on demand for the tensor path.
+// ---------------------------------------------------------------------------------------------
+struct Histogram {
+    int64_t K = 0, Kp = 0;
+    int32_t N = 0;           // spins
+    int32_t Fb = 0;          // padded rows of `base`
+    double M = 0.0;          // sum of counts (num_samples of data_info)
+    double wmax = 0.0;       // max_k c_k / M
+    DevBuf<int8_t> base;
+    DevBuf<double> w64;      // [Kp] c_k / M
+    DevBuf<float> w32;       // [Kp]
+    int32_t mb_order = 0, mb_F = 0, mb_Fp = 0;
+    DevBuf<int8_t> mb;
+    DevBuf<int8_t> P;        // transposed copy of whichever feature matrix was last requested
+    const int8_t* P_of = nullptr;
+};
+
+// One batched solve: Nn node problems over a shared +-1 feature matrix Q [Fp x Kp].
+//   minimise over x_u:  sum_k w_k g( s_u[k] * sum_f Q[f,k] x_u[f] ) + lambda * sum_{pen==L1} |x_u[f]|
+struct NodeProblem {
+    Histogram* hist = nullptr;
+    const int8_t* Q = nullptr;      // feature matrix (hist->base or hist->mb)
+    int32_t F = 0, Fp = 0;
+    int32_t form = 0;
+    double lambda = 0.0;
+    int32_t Nn = 0;                 // nodes in this shard
+    DevBuf<int32_t> spin_row;       // [Nn] row of hist->base that holds s_u
+    DevBuf<uint8_t> pen;            // [Nn x Fp] penalty class per coordinate (padded features = PEN_ZERO)
+};
+
+struct SolveResult {
+    DevBuf<double> x;         // [Nn x Fp]
+    DevBuf<double> objective; // [Nn]  f_u(x) + lambda*|x_pen|_1
+    int iterations = 0, n_fg = 0, n_f = 0, n_unconverged = 0;
+    double max_residual = 0.0;
+};
+
+// --- pack.cu
+void hist_from_device(Histogram& h, const double* d_counts, const int8_t* d_spins, int64_t K, int32_t N,
+                      int64_t ld, cudaStream_t st);
+// multibody base features: all subsets of size <= order-1 of the N spins (subset {} = constant).
+// h_subsets: [F x (order-1)] 0-based spin ids, -1 padded.
+void build_multibody_features(Histogram& h, int order, const std::vector<int32_t>& h_subsets, int F,
+                              cudaStream_t st);
+// sample-major copy [Kp x Fp] of Q [Fp x Kp] (cached in h.P)
+const int8_t* ensure_P(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st);
+
+// --- newton.cu : fp64 proximal-Newton / barrier-Newton for small feature counts
+constexpr int NEWTON_MAX_F = 64;
+void solve_newton(const NodeProblem& p, const gml_b200_opts& o, SolveResult& r, cudaStream_t st);
+
+// --- fista.cu : batched FISTA driver over an evaluation backend
+void solve_fista(const NodeProblem& p, const gml_b200_opts& o, int backend, SolveResult& r, cudaStream_t st);
+
+// --- evaluation backends (objective / gradient passes over the histogram)
+struct EvalBackend {
+    virtual ~EvalBackend() {}
+    // Evaluate at point x [Nn x Fp] (double).  f_out[Nn] receives the smooth objective, g_out
+    // [Nn x Fp] its gradient when want_grad.  lattice() > 0 means x must lie on that grid.
+    virtual void eval(const double* x, bool want_grad, double* f_out, double* g_out, cudaStream_t st) = 0;
+    virtual double lattice() const { return 0.0; }
+};
+EvalBackend* make_backend_cc(const NodeProblem& p, cudaStream_t st);
+EvalBackend* make_backend_tc(const NodeProblem& p, cudaStream_t st);
+
+// --- output.cu
+void symmetrize_rowmajor(double* d_theta, int N, cudaStream_t st);
+
+// --- sampler.cu
+void sample_gibbs(int N, const int32_t* d_row_ptr, const int32_t* d_col, const float* d_J, const float* d_h,
+                  int max_deg, int64_t n_samples, int sweeps, uint64_t seed, int8_t* d_spins, int64_t ld,
+                  cudaStream_t st);
+
+}  // namespace gml

@@ -1,0 +1,179 @@
+// K4: batched FISTA driver.  All Nn node problems advance together; every node carries its own
+// Lipschitz estimate L_u, momentum t_u, restart and convergence state, so there is no host decision
+// inside a round:
+//     trial   Z_u = prox_{lambda/L_u}(Y_u - G_u/L_u)            (soft-threshold on PEN_L1 coordinates)
+//     f(Z)    one objective-only pass over the histogram
+//     accept  sufficient decrease f(Z) <= f(Y) + <G,Z-Y> + L/2|Z-Y|^2 ?  yes: momentum/restart/
+//             convergence, no: L_u *= 2 and the node simply retries next round
+//     f,G(Y)  one full pass
+// The problem solved per node is the reference's (src/GraphicalModelLearning.jl:169-177 etc.) with
+// the slack variables z eliminated: min f_u(x) + lambda*sum_{pen} |x_j|.
+#include "common.cuh"
+
+#include <memory>
+
+namespace gml {
+namespace {
+
+struct FistaState {
+    int Nn, Fp;
+    double lambda, tol, lattice_inv, lattice, eps_f;
+    const uint8_t* pen;
+    double *X, *Z, *Y, *G;
+    double *fY, *fZ, *fX, *L, *t, *q, *c, *gmap, *obj;
+    int* status;      // 0 active, 1 converged
+    int* n_active;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    return s;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s = fmax(s, red[i]);
+    return s;
+}
+
+__device__ __forceinline__ double snap(double v, const FistaState& s) {
+    return s.lattice_inv > 0.0 ? rint(v * s.lattice_inv) * s.lattice : v;
+}
+
+__global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
+    const int u = blockIdx.x;
+    if (s.status[u]) return;
+    __shared__ double red[4];
+    const double L = s.L[u], thr = s.lambda / L;
+    const int64_t o = (int64_t)u * s.Fp;
+    double q1 = 0.0, q2 = 0.0, dm = 0.0;
+    for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
+        const uint8_t pc = s.pen[o + f];
+        const double y = s.Y[o + f], g = s.G[o + f];
+        double z = 0.0;
+        if (pc != PEN_ZERO) {
+            z = y - g / L;
+            if (pc == PEN_L1) { const double a = fabs(z) - thr; z = a > 0.0 ? copysign(a, z) : 0.0; }
+            z = snap(z, s);
+        }
+        s.Z[o + f] = z;
+        const double d = z - y;
+        q1 += g * d; q2 += d * d; dm = fmax(dm, fabs(d));
+    }
+    q1 = block_sum(q1, red); q2 = block_sum(q2, red); dm = block_max(dm, red);
+    if (threadIdx.x == 0) {
+        s.q[u] = q1 + 0.5 * L * q2;
+        s.c[u] = 0.5 * L * q2;
+        s.gmap[u] = L * dm;
+    }
+}
+
+__global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
+    const int u = blockIdx.x;
+    if (s.status[u]) return;
+    __shared__ double red[4];
+    const int64_t o = (int64_t)u * s.Fp;
+    const double fY = s.fY[u], fZ = s.fZ[u];
+    const double noise = s.eps_f * fmax(fabs(fY), 1e-300);
+    const bool ok = (fZ <= fY + s.q[u] + noise) && isfinite(fZ);
+    if (!ok) {
+        if (threadIdx.x == 0) { s.L[u] *= 2.0; atomicAdd(s.n_active, 1); }
+        return;
+    }
+    // gradient-scheme adaptive restart: <Y - Z, Z - X> > 0
+    double r = 0.0;
+    for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) r += (s.Y[o + f] - s.Z[o + f]) * (s.Z[o + f] - s.X[o + f]);
+    r = block_sum(r, red);
+    const double t = s.t[u];
+    const bool restart = r > 0.0;
+    const double tn = restart ? 1.0 : 0.5 * (1.0 + sqrt(1.0 + 4.0 * t * t));
+    const double beta = restart ? 0.0 : (t - 1.0) / tn;
+    const bool conv = s.gmap[u] <= s.tol;
+    double l1 = 0.0;
+    for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
+        const double z = s.Z[o + f], x = s.X[o + f];
+        s.Y[o + f] = conv ? z : snap(z + beta * (z - x), s);
+        s.X[o + f] = z;
+        if (s.pen[o + f] == PEN_L1) l1 += fabs(z);
+    }
+    l1 = block_sum(l1, red);
+    if (threadIdx.x == 0) {
+        s.t[u] = tn;
+        s.fX[u] = fZ;
+        s.obj[u] = fZ + s.lambda * l1;
+        if (s.c[u] > 100.0 * noise) s.L[u] *= 0.98;   // only relax L while the test is meaningful
+        if (conv) s.status[u] = 1; else atomicAdd(s.n_active, 1);
+    }
+}
+
+__global__ void fista_init_kernel(FistaState s, double L0) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= s.Nn) return;
+    s.L[u] = L0; s.t[u] = 1.0; s.status[u] = 0; s.gmap[u] = 1e300; s.obj[u] = 0.0; s.fX[u] = 0.0;
+}
+
+}  // namespace
+
+void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, SolveResult& r, cudaStream_t st) {
+    const int Nn = prob.Nn, Fp = prob.Fp;
+    std::unique_ptr<EvalBackend> be(backend == GML_B200_SOLVER_FISTA_TC ? make_backend_tc(prob, st)
+                                                                        : make_backend_cc(prob, st));
+    const size_t nx = (size_t)Nn * Fp;
+    DevBuf<double> Z, Y, G, fY, fZ, fX, L, t, q, c, gmap;
+    DevBuf<int> status, n_active;
+    r.x.alloc(nx); r.objective.alloc(Nn);
+    Z.alloc(nx); Y.alloc(nx); G.alloc(nx);
+    fY.alloc(Nn); fZ.alloc(Nn); fX.alloc(Nn); L.alloc(Nn); t.alloc(Nn); q.alloc(Nn); c.alloc(Nn); gmap.alloc(Nn);
+    status.alloc(Nn); n_active.alloc(1);
+    GML_CUDA(cudaMemsetAsync(r.x.p, 0, nx * sizeof(double), st));
+    GML_CUDA(cudaMemsetAsync(Y.p, 0, nx * sizeof(double), st));
+    GML_CUDA(cudaMemsetAsync(Z.p, 0, nx * sizeof(double), st));
+
+    FistaState s{};
+    s.Nn = Nn; s.Fp = Fp; s.lambda = prob.lambda;
+    s.tol = o.tol > 0 ? o.tol : 1e-6;
+    s.lattice = be->lattice();
+    s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
+    s.eps_f = backend == GML_B200_SOLVER_FISTA_TC ? 2e-8 : 2e-7;
+    s.pen = prob.pen.p;
+    s.X = r.x.p; s.Z = Z.p; s.Y = Y.p; s.G = G.p;
+    s.fY = fY.p; s.fZ = fZ.p; s.fX = fX.p; s.L = L.p; s.t = t.p; s.q = q.p; s.c = c.p; s.gmap = gmap.p;
+    s.obj = r.objective.p; s.status = status.p; s.n_active = n_active.p;
+
+    fista_init_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s, 1.0);
+    GML_LAUNCHED();
+    be->eval(Y.p, true, fY.p, G.p, st);
+    int n_fg = 1, n_f = 0, it = 0, active = Nn;
+    const int max_iter = o.max_iter > 0 ? o.max_iter : 5000;
+    for (; it < max_iter; ++it) {
+        fista_trial_kernel<<<Nn, 128, 0, st>>>(s);
+        GML_LAUNCHED();
+        be->eval(Z.p, false, fZ.p, nullptr, st); ++n_f;
+        GML_CUDA(cudaMemsetAsync(n_active.p, 0, sizeof(int), st));
+        fista_accept_kernel<<<Nn, 128, 0, st>>>(s);
+        GML_LAUNCHED();
+        GML_CUDA(cudaMemcpyAsync(&active, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GML_CUDA(cudaStreamSynchronize(st));
+        if (o.verbose > 1) fprintf(stderr, "[gml_b200] fista round %d active %d\n", it, active);
+        if (active == 0) { ++it; break; }
+        be->eval(Y.p, true, fY.p, G.p, st); ++n_fg;
+    }
+    std::vector<double> hg(Nn);
+    std::vector<int> hs(Nn);
+    GML_CUDA(cudaMemcpyAsync(hg.data(), gmap.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost, st));
+    GML_CUDA(cudaMemcpyAsync(hs.data(), status.p, sizeof(int) * Nn, cudaMemcpyDeviceToHost, st));
+    GML_CUDA(cudaStreamSynchronize(st));
+    double mr = 0.0; int unconv = 0;
+    for (int u = 0; u < Nn; ++u) { mr = std::max(mr, hg[u]); unconv += hs[u] ? 0 : 1; }
+    r.iterations = it; r.n_fg = n_fg; r.n_f = n_f; r.n_unconverged = unconv; r.max_residual = mr;
+}
+
+}  // namespace gml

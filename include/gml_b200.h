@@ -1,0 +1,149 @@
+/*
+ * gml_b200.h -- C ABI of libgml_b200.so, the B200-native replacement for the per-node convex fits
+ * behind `learn(samples, formulation, method)` of lanl-ansi/GraphicalModelLearning.jl (v0.2.2).
+ *
+ * The reference has no FFI of its own: the hot path is Julia code that hands each node's problem to
+ * JuMP/Ipopt (src/GraphicalModelLearning.jl:83-152, 154-189, 263-298, 301-336).  The entry points
+ * below are what a new `GMLMethod` subtype binds with `ccall` (see INTEGRATION.md and
+ * graphicalmodellearning.jl_b200/julia/GMLB200.jl); each one cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C types only, no exceptions cross the boundary; every function returns a status code and
+ *     `gml_b200_last_error()` holds a thread-local message for the last non-zero status.
+ *   - the caller owns every host buffer; the library owns all device memory behind a handle.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     GML_B200_ECUDA.
+ *
+ * Histogram layout (the reference's `samples` matrix, src/GraphicalModelLearning.jl:76-81):
+ *   counts[k]            = samples[k,1]                      (double, > 0)
+ *   spins[i*ld + k]      = samples[k,1+i]  in {-1,+1}         (int8, spin-major, ld >= K)
+ * which is exactly the memory of Julia's column-major `Int8.(samples[:,2:end])`.
+ */
+#ifndef GML_B200_H
+#define GML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GML_B200_OK 0
+#define GML_B200_EINVAL 1   /* invalid input (shape, spin not +-1, count <= 0, unsupported option) */
+#define GML_B200_ECUDA 2    /* CUDA runtime / driver error, or no device */
+#define GML_B200_ENOTCONV 3 /* a node did not reach `tol` within `max_iter`; mirrors the reference's
+                               @assert termination_status == LOCALLY_SOLVED (:127,180,289,327) */
+
+/* formulation ids: RISE (:154), logRISE (:263), RPLE (:301) */
+#define GML_B200_RISE 0
+#define GML_B200_LOGRISE 1
+#define GML_B200_RPLE 2
+
+/* solver selection */
+#define GML_B200_SOLVER_AUTO 0
+#define GML_B200_SOLVER_NEWTON 1   /* fp64 proximal-Newton, features <= 64 (small problems)        */
+#define GML_B200_SOLVER_FISTA_CC 2 /* batched FISTA, CUDA-core fp32 contractions                   */
+#define GML_B200_SOLVER_FISTA_TC 3 /* batched FISTA, tcgen05 (int8 limb) tensor-core contractions  */
+
+typedef struct gml_b200_opts {
+    double tol;         /* stopping tolerance (max-norm of prox-gradient mapping / Newton step); default 1e-6 FISTA, 1e-12 Newton */
+    double barrier_mu;  /* 0 = exact L1 minimiser; > 0 = Ipopt-compatible log-barrier point at this mu (Newton solver only) */
+    int32_t max_iter;   /* default 5000 */
+    int32_t solver;     /* GML_B200_SOLVER_* */
+    int32_t device;     /* CUDA device ordinal */
+    int32_t node_begin; /* node shard [node_begin, node_end); node_end <= 0 means N */
+    int32_t node_end;
+    int32_t verbose;
+    void* stream;       /* cudaStream_t to launch on; NULL = the handle's own stream */
+    int32_t reserved[8];
+} gml_b200_opts;
+
+typedef struct gml_b200_stats {
+    int32_t solver_used;
+    int32_t iterations;       /* outer iterations (max over nodes) */
+    int32_t n_fg_passes;      /* full objective+gradient passes over the histogram */
+    int32_t n_f_passes;       /* objective-only passes */
+    int32_t n_unconverged;    /* nodes that missed tol */
+    int32_t reserved_i;
+    int64_t kernel_launches;  /* kernels of this library launched by the call */
+    double evals;             /* node*sample evals = nodes*K*(n_fg + 0.5*n_f)   */
+    double pack_ms;           /* device: validate + layout build */
+    double h2d_ms;            /* host->device copies */
+    double solve_ms;          /* device-timed solver (CUDA events on the launch stream) */
+    double d2h_ms;
+    double total_ms;          /* host wall clock of the whole call */
+    double max_residual;      /* largest final stopping residual over nodes */
+    double reserved_d[4];
+} gml_b200_stats;
+
+typedef struct gml_b200_handle gml_b200_handle;
+
+const char* gml_b200_version(void);
+const char* gml_b200_last_error(void);
+int gml_b200_device_count(void);
+void gml_b200_opts_default(gml_b200_opts* opts);
+
+/* ---- one-shot entry points (host buffers in, host buffers out) ------------------------------- */
+
+/* Replaces learn(samples, ::RISE/::logRISE/::RPLE, ::NLP)  (src/GraphicalModelLearning.jl:154-189,
+ * 263-298, 301-336).  `lambda` is the reference's regularizer*sqrt(log(N^2/0.05)/M) (:157), computed
+ * by the caller.  out_theta is N x N COLUMN-major (Julia native): out_theta[u + N*i] = x_u[i], the
+ * diagonal holds the fields (:181); symmetrised as 0.5*(R+R') iff symmetrize != 0 (:184-186). */
+int gml_b200_learn_pairwise(const double* counts, const int8_t* spins, int64_t K, int32_t N, int64_t ld,
+                            int32_t formulation, double lambda, int32_t symmetrize,
+                            const gml_b200_opts* opts, double* out_theta, double* out_objective /* N, nullable */,
+                            gml_b200_stats* stats /* nullable */);
+
+/* Replaces the per-node core of learn(samples, ::multiRISE, ::NLP) (src/GraphicalModelLearning.jl:83-133).
+ * out_vals[u*n_keys + f] is node u's value for its f-th key in the reference's own key order:
+ * (u,), then (u,j) j ascending, then (u,j<k) lexicographic, ... (src/GraphicalModelLearning.jl:94-104,
+ * src/models.jl:228-246).  n_keys = gml_b200_multibody_num_keys(N, order).  Symmetrisation by key
+ * (:135-149) is Dict work and stays with the caller. */
+int gml_b200_learn_multibody(const double* counts, const int8_t* spins, int64_t K, int32_t N, int64_t ld,
+                             int32_t interaction_order, double lambda, const gml_b200_opts* opts,
+                             double* out_vals, double* out_objective /* N, nullable */, gml_b200_stats* stats);
+
+int64_t gml_b200_multibody_num_keys(int32_t N, int32_t interaction_order);
+
+/* ---- handle API: keep the histogram resident in HBM across solves ----------------------------- */
+
+int gml_b200_create(gml_b200_handle** h, int32_t device);
+void gml_b200_destroy(gml_b200_handle* h);
+
+/* data_info (src/GraphicalModelLearning.jl:76-81) + device layout build.  Host pointers. */
+int gml_b200_upload_histogram(gml_b200_handle* h, const double* counts, const int8_t* spins,
+                              int64_t K, int32_t N, int64_t ld, gml_b200_stats* stats);
+/* Same, but counts/spins already live in device memory of h's device (no host copies). */
+int gml_b200_attach_histogram_device(gml_b200_handle* h, const double* d_counts, const int8_t* d_spins,
+                                     int64_t K, int32_t N, int64_t ld, gml_b200_stats* stats);
+/* sum of counts of the resident histogram (num_samples of data_info) */
+double gml_b200_num_samples(const gml_b200_handle* h);
+
+/* Solve on the resident histogram, result to host (same layout as gml_b200_learn_pairwise). */
+int gml_b200_solve_pairwise(gml_b200_handle* h, int32_t formulation, double lambda, int32_t symmetrize,
+                            const gml_b200_opts* opts, double* out_theta, double* out_objective,
+                            gml_b200_stats* stats);
+/* Solve the node shard [opts->node_begin, opts->node_end) and leave the rows in device memory:
+ * d_out_rows is (node_end-node_begin) x N ROW-major (row u contiguous) so that shards of several
+ * GPUs concatenate with one all-gather.  No symmetrisation here. */
+int gml_b200_solve_pairwise_device(gml_b200_handle* h, int32_t formulation, double lambda,
+                                   const gml_b200_opts* opts, double* d_out_rows, double* d_out_objective /* nullable */,
+                                   gml_b200_stats* stats);
+int gml_b200_solve_multibody(gml_b200_handle* h, int32_t interaction_order, double lambda,
+                             const gml_b200_opts* opts, double* out_vals, double* out_objective,
+                             gml_b200_stats* stats);
+
+/* 0.5*(R + R') in place on a ROW-major N x N device matrix (src/GraphicalModelLearning.jl:184-186). */
+int gml_b200_symmetrize_device(double* d_theta, int32_t N, void* stream);
+
+/* ---- input generator: multi-chain Gibbs sampler for pairwise +-1 models ----------
+ * Fills d_spins (int8, spin-major, ld >= n_samples) with one sample per chain after `sweeps` full
+ * sweeps from a random start.  Neighbour lists in CSR form on the host.  Deterministic in `seed`. */
+int gml_b200_sample_gibbs_device(int32_t device, int32_t N, const int32_t* row_ptr, const int32_t* col_idx,
+                                 const float* coupling, const float* field, int64_t n_samples,
+                                 int32_t sweeps, uint64_t seed, int8_t* d_spins, int64_t ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GML_B200_H */
