@@ -262,3 +262,84 @@ def learn(samples, formulation: Optional[GMLFormulation] = None, method: Optiona
         raise TypeError("method must be a GMLMethod")
     counts, spins = pack_histogram(samples)
     return learn_packed(counts, spins, formulation, method, return_info=return_info)
+
+
+class Session:
+    """Handle API (include/gml_b200.h): keeps the histogram resident in HBM across calls."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.gml_b200_create(ctypes.byref(self._h), device))
+        self.device = device
+        self.N = self.K = 0
+        self.upload_stats: dict = {}
+
+    def close(self):
+        if self._h:
+            self._lib.gml_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def upload(self, counts: np.ndarray, spins: np.ndarray):
+        N, K = spins.shape
+        assert counts.dtype == np.float64 and spins.dtype == np.int8 and spins.strides[1] == 1
+        st = _lib.Stats()
+        _lib.check(self._lib.gml_b200_upload_histogram(self._h, _ptr(counts), _ptr(spins), K, N,
+                                                       spins.strides[0], ctypes.byref(st)))
+        self.N, self.K, self.upload_stats = N, K, st.as_dict()
+        return self
+
+    def attach_device(self, d_counts_ptr: int, d_spins_ptr: int, K: int, N: int, ld: int):
+        st = _lib.Stats()
+        _lib.check(self._lib.gml_b200_attach_histogram_device(self._h, ctypes.c_void_p(d_counts_ptr),
+                                                              ctypes.c_void_p(d_spins_ptr), K, N, ld, ctypes.byref(st)))
+        self.N, self.K, self.upload_stats = N, K, st.as_dict()
+        return self
+
+    @property
+    def num_samples(self) -> float:
+        return float(self._lib.gml_b200_num_samples(self._h))
+
+    def solve_pairwise(self, formulation, method: B200, lam: Optional[float] = None, return_info=False):
+        N = self.N
+        form_id = {RISE: 0, logRISE: 1, RPLE: 2}[type(formulation)]
+        if lam is None:
+            lam = regularizer_lambda(formulation.regularizer, N, self.num_samples)
+        theta = np.zeros((N, N), order="F")
+        obj = np.zeros(N)
+        st = _lib.Stats()
+        opts = method._opts()
+        rc = self._lib.gml_b200_solve_pairwise(self._h, form_id, lam, int(bool(formulation.symmetrization)),
+                                               ctypes.byref(opts), _ptr(theta), _ptr(obj), ctypes.byref(st))
+        method.last_stats = st.as_dict()
+        _lib.check(rc)
+        out = np.ascontiguousarray(theta)
+        return (out, {"lambda": lam, "objective": obj, **method.last_stats}) if return_info else out
+
+    def solve_pairwise_device(self, formulation, method: B200, d_rows_ptr: int, node_begin: int, node_end: int,
+                              lam: Optional[float] = None, stream: int = 0, d_obj_ptr: int = 0):
+        form_id = {RISE: 0, logRISE: 1, RPLE: 2}[type(formulation)]
+        if lam is None:
+            lam = regularizer_lambda(formulation.regularizer, self.N, self.num_samples)
+        st = _lib.Stats()
+        opts = method._opts(node_begin, node_end, stream)
+        rc = self._lib.gml_b200_solve_pairwise_device(self._h, form_id, lam, ctypes.byref(opts),
+                                                      ctypes.c_void_p(d_rows_ptr),
+                                                      ctypes.c_void_p(d_obj_ptr) if d_obj_ptr else None, ctypes.byref(st))
+        method.last_stats = st.as_dict()
+        _lib.check(rc)
+        return method.last_stats
+
+    def eval_pairwise(self, formulation, x: np.ndarray, backend: str = "fista_tc", want_grad: bool = True):
+        """f_u and grad f_u at rows x [N x (N+1)] (couplings then field)."""
+        form_id = {RISE: 0, logRISE: 1, RPLE: 2}[type(formulation)]
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == (self.N, self.N + 1)
+        f = np.zeros(self.N)
+        g = np.zeros_like(x) if want_grad else None
+        opts = B200(solver=backend)._opts()
+        _lib.check(self._lib.gml_b200_eval_pairwise(self._h, form_id, ctypes.byref(opts), _ptr(x), _ptr(f),
+                                                    _ptr(g) if want_grad else None))
+        return f, g

@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
                 print(log, file=sys.stderr)
     objs = [OBJ / (s.stem + ".o") for s in sources]
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart", "-lcuda"]
+        cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

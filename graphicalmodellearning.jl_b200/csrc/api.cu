@@ -446,6 +446,52 @@ int gml_b200_solve_multibody(gml_b200_handle* h, int32_t order, double lambda, c
     });
 }
 
+int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b200_opts* opts, const double* x,
+                           double* f_out, double* g_out) {
+    return guarded([&] {
+        GML_REQUIRE(h && x && f_out, "null argument");
+        GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
+        GML_REQUIRE(formulation >= GML_B200_RISE && formulation <= GML_B200_RPLE, "unknown formulation id");
+        g_launches = 0;
+        gml_b200_opts o; fill_opts(o, opts);
+        GML_REQUIRE(o.solver == GML_B200_SOLVER_FISTA_CC || o.solver == GML_B200_SOLVER_FISTA_TC,
+                    "eval needs solver = FISTA_CC or FISTA_TC");
+        GML_CUDA(cudaSetDevice(h->device));
+        cudaStream_t st = stream_of(h, o);
+        Histogram& hist = h->hist;
+        const int N = hist.N, F = N + 1;
+        const int nb = o.node_begin, ne = o.node_end > 0 ? o.node_end : N;
+        GML_REQUIRE(nb >= 0 && ne <= N && nb < ne, "node shard out of range");
+        NodeProblem p;
+        p.hist = &hist; p.Q = hist.base.p; p.F = F; p.Fp = hist.Fb;
+        p.form = formulation; p.lambda = 0.0; p.Nn = ne - nb;
+        p.spin_row.alloc(p.Nn); p.pen.alloc((size_t)p.Nn * p.Fp);
+        pairwise_setup_kernel<<<p.Nn, 128, 0, st>>>(N, p.Fp, nb, p.Nn, p.spin_row.p, p.pen.p);
+        GML_LAUNCHED();
+        std::unique_ptr<EvalBackend> be(o.solver == GML_B200_SOLVER_FISTA_TC ? make_backend_tc(p, st) : make_backend_cc(p, st));
+        std::vector<double> hx((size_t)p.Nn * p.Fp, 0.0);
+        const double lat = be->lattice();
+        for (int u = 0; u < p.Nn; ++u)
+            for (int f = 0; f < F; ++f) {
+                double v = (f == nb + u) ? 0.0 : x[(size_t)u * F + f];
+                if (lat > 0.0) v = std::nearbyint(v / lat) * lat;
+                hx[(size_t)u * p.Fp + f] = v;
+            }
+        DevBuf<double> dx, df, dg;
+        dx.alloc(hx.size()); df.alloc(p.Nn); dg.alloc(hx.size());
+        GML_CUDA(cudaMemcpyAsync(dx.p, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice, st));
+        be->eval(dx.p, g_out != nullptr, df.p, dg.p, st);
+        GML_CUDA(cudaMemcpyAsync(f_out, df.p, sizeof(double) * p.Nn, cudaMemcpyDeviceToHost, st));
+        if (g_out) {
+            GML_CUDA(cudaMemcpyAsync(hx.data(), dg.p, sizeof(double) * hx.size(), cudaMemcpyDeviceToHost, st));
+            GML_CUDA(cudaStreamSynchronize(st));
+            for (int u = 0; u < p.Nn; ++u)
+                for (int f = 0; f < F; ++f) g_out[(size_t)u * F + f] = (f == nb + u) ? 0.0 : hx[(size_t)u * p.Fp + f];
+        }
+        GML_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
 int gml_b200_symmetrize_device(double* d_theta, int32_t N, void* stream) {
     return guarded([&] {
         GML_REQUIRE(d_theta && N >= 1, "bad argument");

@@ -390,7 +390,8 @@ __global__ void newton_update_kernel(NewtonParams p, int form, int n_alpha) {
         const double fv = (form == GML_B200_LOGRISE) ? log(s) : s;
         const double merit = fv + penv;
         const double f0 = p.fcur[u];
-        const double slack = (p.barrier ? 1e-15 : 1e-16) * fabs(f0);
+        // fp64 summation noise of the two passes (different reduction orders) is ~1e-14 |f|
+        const double slack = 1e-13 * fmax(fabs(f0), 1.0);
         last_merit = merit; last_alpha = alpha;
         if (merit <= f0 + 1e-4 * alpha * p.slope[u] + slack) { found = true; chosen = alpha; }
         else alpha *= 0.5;

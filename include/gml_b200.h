@@ -133,6 +133,13 @@ int gml_b200_solve_multibody(gml_b200_handle* h, int32_t interaction_order, doub
                              const gml_b200_opts* opts, double* out_vals, double* out_objective,
                              gml_b200_stats* stats);
 
+/* Objective and gradient of the smooth part f_u (src/GraphicalModelLearning.jl:170 / 279 / 317) for all nodes of
+ * the shard at a caller-supplied point.  x, g_out: (node_end-node_begin) x (N+1) row-major host arrays, feature
+ * order = couplings to spins 0..N-1 (the self entry is ignored / returns 0), then the local field.  `solver`
+ * selects the contraction backend (GML_B200_SOLVER_FISTA_CC or _TC; the TC backend rounds x to its 2^-24 lattice). */
+int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b200_opts* opts, const double* x,
+                           double* f_out, double* g_out /* nullable */);
+
 /* 0.5*(R + R') in place on a ROW-major N x N device matrix (src/GraphicalModelLearning.jl:184-186). */
 int gml_b200_symmetrize_device(double* d_theta, int32_t N, void* stream);
 

@@ -180,7 +180,8 @@ static int solve_exact(const node_problem* p, const uint8_t* pen, double lam, do
         for (;;) {
             for (int j = 0; j < F; ++j) xn[j] = x[j] + alpha * d[j];
             double Fn = eval_f(p, xn) + lam * l1_pen(xn, pen, F); ++*n_f;
-            if (Fn <= Fx + 1e-4 * alpha * delta_model + 1e-16 * fabs(Fx) || alpha < 1e-10) break;
+            /* slack: float64 summation noise of eval_f over K terms */
+            if (Fn <= Fx + 1e-4 * alpha * delta_model + 1e-13 * fmax(fabs(Fx), 1.0) || alpha < 1e-10) break;
             alpha *= 0.5;
         }
         memcpy(x, xn, sizeof(double) * F);
@@ -253,7 +254,7 @@ static int solve_barrier(const node_problem* p, const uint8_t* pen, double lam, 
         for (;;) {
             for (int j = 0; j < F; ++j) xn[j] = x[j] + alpha * d[j];
             double m = eval_f(p, xn) + barrier_sum(xn, pen, F, lam, mu); ++*n_f;
-            if (m <= m0 + 1e-4 * alpha * slope + 1e-15 * fabs(m0) || alpha < 1e-12) break;
+            if (m <= m0 + 1e-4 * alpha * slope + 1e-13 * fmax(fabs(m0), 1.0) || alpha < 1e-12) break;
             alpha *= 0.5;
         }
         double step = 0.0;

@@ -193,7 +193,7 @@ def solve_node_exact(form, stat, w, lam, pen, x0=None, tol=1e-13, max_outer=200)
         while True:
             xn = x + alpha * d
             Fn = smooth_value(form, xn, stat, w) + lam * np.abs(xn[pen]).sum()
-            if Fn <= Fx + 1e-4 * alpha * delta_model + 1e-16 * abs(Fx) or alpha < 1e-10:
+            if Fn <= Fx + 1e-4 * alpha * delta_model + 1e-13 * max(abs(Fx), 1.0) or alpha < 1e-10:
                 break
             alpha *= 0.5
         x = xn
@@ -238,7 +238,7 @@ def solve_node_barrier(form, stat, w, lam, pen, mu, x0, tol=1e-15, max_iter=200)
         alpha = 1.0
         while True:
             xn = x + alpha * d
-            if merit(xn) <= m0 + 1e-4 * alpha * slope + 1e-15 * abs(m0) or alpha < 1e-12:
+            if merit(xn) <= m0 + 1e-4 * alpha * slope + 1e-13 * max(abs(m0), 1.0) or alpha < 1e-12:
                 break
             alpha *= 0.5
         x = xn

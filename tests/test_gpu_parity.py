@@ -51,9 +51,11 @@ def test_c1_random_ising(form, solver):
     """BASELINE config C1: N=16 random Ising, 1e5 exact samples."""
     _, hist = histogram_c1()
     ref, rinfo = c.learn_pairwise(hist, form, return_info=True)
-    tol = 0.0 if solver == "newton" else 1e-7
+    # FISTA: default tol 1e-6 for the CUDA-core backend (fp32 gradient noise floor ~2e-6), 1e-7 for the
+    # fixed-point tensor-core backend
+    tol = {"newton": 0.0, "fista_cc": 0.0, "fista_tc": 1e-7}[solver]
     got, info = gml_b200.learn(hist, FORMS[form](), B200(solver=solver, tol=tol), return_info=True)
-    bar = 1e-9 if solver == "newton" else 2e-5
+    bar = {"newton": 1e-9, "fista_cc": 5e-5, "fista_tc": 2e-6}[solver]
     assert np.abs(got - ref).max() <= bar
     assert np.allclose(info["objective"], rinfo["objective"], rtol=1e-9 if solver == "newton" else 1e-6, atol=0)
 
@@ -62,8 +64,8 @@ def test_c1_random_ising(form, solver):
 def test_unsymmetrised_and_rows(solver):
     _, hist = histogram_c1(n=12, m_samples=20000, seed=5)
     ref = c.learn_pairwise(hist, "RISE", 0.3, False)
-    got = gml_b200.learn(hist, RISE(0.3, False), B200(solver=solver, tol=1e-7))
-    assert np.abs(got - ref).max() <= 2e-5
+    got = gml_b200.learn(hist, RISE(0.3, False), B200(solver=solver))
+    assert np.abs(got - ref).max() <= 5e-5
     assert not np.allclose(got, got.T)
 
 
@@ -106,8 +108,8 @@ def test_multirise_order3_larger_fista():
     hist = o.sample_exact(terms, n, 200_000, np.random.default_rng(31))
     base = gml_b200.learn(hist, multiRISE(0.4, False, 3), B200(solver="newton"))
     for solver in ("fista_cc", "fista_tc"):
-        got = gml_b200.learn(hist, multiRISE(0.4, False, 3), B200(solver=solver, tol=1e-7))
-        assert max(abs(got[k] - base[k]) for k in base.terms) <= 2e-5
+        got = gml_b200.learn(hist, multiRISE(0.4, False, 3), B200(solver=solver))
+        assert max(abs(got[k] - base[k]) for k in base.terms) <= 5e-5
 
 
 @pytest.mark.parametrize("n_samples,thr", [(1000, 0.15), (10000, 0.05)])
