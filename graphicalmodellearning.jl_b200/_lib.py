@@ -18,7 +18,7 @@ EXPORTS = (
     "gml_b200_learn_pairwise", "gml_b200_learn_multibody", "gml_b200_multibody_num_keys",
     "gml_b200_create", "gml_b200_destroy", "gml_b200_upload_histogram",
     "gml_b200_attach_histogram_device", "gml_b200_num_samples", "gml_b200_solve_pairwise",
-    "gml_b200_solve_pairwise_device", "gml_b200_solve_multibody", "gml_b200_eval_pairwise",
+    "gml_b200_solve_pairwise_device", "gml_b200_solve_multibody", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
     "gml_b200_symmetrize_device",
     "gml_b200_sample_gibbs_device",
 )
@@ -41,7 +41,9 @@ class Stats(ctypes.Structure):
                 ("max_residual", ctypes.c_double), ("reserved_d", ctypes.c_double * 4)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
+        d["energy_fg_ms"], d["grad_ms"], d["energy_f_ms"] = self.reserved_d[0], self.reserved_d[1], self.reserved_d[2]
+        return d
 
 
 class GMLB200Error(RuntimeError):
@@ -89,6 +91,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gml_b200_solve_pairwise_device.argtypes = [vp, c.c_int32, c.c_double, op, vp, vp, sp]
     lib.gml_b200_solve_multibody.argtypes = [vp, c.c_int32, c.c_double, op, vp, vp, sp]
     lib.gml_b200_eval_pairwise.argtypes = [vp, c.c_int32, op, vp, vp, vp]
+    lib.gml_b200_bench_passes.argtypes = [vp, c.c_int32, op, c.c_int32, vp]
     lib.gml_b200_symmetrize_device.argtypes = [vp, c.c_int32, vp]
     lib.gml_b200_sample_gibbs_device.argtypes = [c.c_int32, c.c_int32, vp, vp, vp, vp, c.c_int64, c.c_int32,
                                                  c.c_uint64, vp, c.c_int64, vp]

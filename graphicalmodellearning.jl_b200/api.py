@@ -80,6 +80,7 @@ class B200(GMLMethod):
     barrier_mu: float = 0.0
     device: int = 0
     verbose: int = 0
+    profile: bool = False         # time the contraction kernels with CUDA events (stats energy_*_ms / grad_ms)
     last_stats: dict = field(default_factory=dict, repr=False, compare=False)
 
     def _opts(self, node_begin: int = 0, node_end: int = 0, stream: int = 0) -> _lib.Opts:
@@ -92,6 +93,7 @@ class B200(GMLMethod):
         o.verbose = int(self.verbose)
         o.node_begin, o.node_end = int(node_begin), int(node_end)
         o.stream = ctypes.c_void_p(stream) if stream else None
+        o.reserved[0] = 1 if self.profile else 0
         return o
 
 
@@ -343,3 +345,11 @@ class Session:
         _lib.check(self._lib.gml_b200_eval_pairwise(self._h, form_id, ctypes.byref(opts), _ptr(x), _ptr(f),
                                                     _ptr(g) if want_grad else None))
         return f, g
+
+    def bench_passes(self, formulation, backend: str = "fista_tc", reps: int = 5, node_begin: int = 0, node_end: int = 0):
+        """Mean device ms of the contraction kernels: dict(energy_full, grad, energy_obj, full_pass_wall)."""
+        form_id = {RISE: 0, logRISE: 1, RPLE: 2}[type(formulation)]
+        out = np.zeros(4)
+        opts = B200(solver=backend)._opts(node_begin, node_end)
+        _lib.check(self._lib.gml_b200_bench_passes(self._h, form_id, ctypes.byref(opts), reps, _ptr(out)))
+        return dict(zip(("energy_full", "grad", "energy_obj", "full_pass_wall"), out.tolist()))

@@ -153,6 +153,7 @@ void finish_stats(gml_b200_stats* stats, const SolveResult& r, int solver_used, 
     stats->d2h_ms = d2h_ms;
     stats->total_ms += now_ms() - t0;
     stats->max_residual = r.max_residual;
+    for (int i = 0; i < 4; ++i) stats->reserved_d[i] = r.profile[i];
 }
 
 void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, const gml_b200_opts& o, int nb, int ne,
@@ -489,6 +490,46 @@ int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b2
                 for (int f = 0; f < F; ++f) g_out[(size_t)u * F + f] = (f == nb + u) ? 0.0 : hx[(size_t)u * p.Fp + f];
         }
         GML_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int gml_b200_bench_passes(gml_b200_handle* h, int32_t formulation, const gml_b200_opts* opts, int32_t reps,
+                          double* out_ms) {
+    return guarded([&] {
+        GML_REQUIRE(h && out_ms && reps >= 1, "bad argument");
+        GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
+        g_launches = 0;
+        gml_b200_opts o; fill_opts(o, opts);
+        GML_REQUIRE(o.solver == GML_B200_SOLVER_FISTA_CC || o.solver == GML_B200_SOLVER_FISTA_TC,
+                    "bench needs solver = FISTA_CC or FISTA_TC");
+        GML_CUDA(cudaSetDevice(h->device));
+        cudaStream_t st = stream_of(h, o);
+        Histogram& hist = h->hist;
+        const int N = hist.N;
+        const int nb = o.node_begin, ne = o.node_end > 0 ? o.node_end : N;
+        GML_REQUIRE(nb >= 0 && ne <= N && nb < ne, "node shard out of range");
+        NodeProblem p;
+        p.hist = &hist; p.Q = hist.base.p; p.F = N + 1; p.Fp = hist.Fb;
+        p.form = formulation; p.lambda = 0.0; p.Nn = ne - nb;
+        p.spin_row.alloc(p.Nn); p.pen.alloc((size_t)p.Nn * p.Fp);
+        pairwise_setup_kernel<<<p.Nn, 128, 0, st>>>(N, p.Fp, nb, p.Nn, p.spin_row.p, p.pen.p);
+        GML_LAUNCHED();
+        std::unique_ptr<EvalBackend> be(o.solver == GML_B200_SOLVER_FISTA_TC ? make_backend_tc(p, st) : make_backend_cc(p, st));
+        DevBuf<double> dx, df, dg;
+        const size_t nx = (size_t)p.Nn * p.Fp;
+        dx.alloc(nx); df.alloc(p.Nn); dg.alloc(nx);
+        GML_CUDA(cudaMemsetAsync(dx.p, 0, sizeof(double) * nx, st));
+        be->eval(dx.p, true, df.p, dg.p, st);    // warm-up
+        be->eval(dx.p, false, df.p, nullptr, st);
+        be->set_profiling(true);
+        EventTimer wall(st);
+        for (int i = 0; i < reps; ++i) be->eval(dx.p, true, df.p, dg.p, st);
+        const double wall_ms = wall.stop();
+        for (int i = 0; i < reps; ++i) be->eval(dx.p, false, df.p, nullptr, st);
+        GML_CUDA(cudaStreamSynchronize(st));
+        double prof[4] = {0, 0, 0, 0};
+        be->collect_profile(prof);
+        out_ms[0] = prof[0] / reps; out_ms[1] = prof[1] / reps; out_ms[2] = prof[2] / reps; out_ms[3] = wall_ms / reps;
     });
 }
 

@@ -86,6 +86,8 @@ struct Histogram {
     DevBuf<int8_t> mb;
     DevBuf<int8_t> P;        // transposed copy of whichever feature matrix was last requested
     const int8_t* P_of = nullptr;
+    DevBuf<int8_t> Qb;       // sample-blocked copy [Kp/128][Fp][128] of the same matrix (tile-contiguous for TMA)
+    const int8_t* Qb_of = nullptr;
 };
 
 // One batched solve: Nn node problems over a shared +-1 feature matrix Q [Fp x Kp].
@@ -102,6 +104,7 @@ struct NodeProblem {
 };
 
 struct SolveResult {
+    double profile[4] = {0, 0, 0, 0};
     DevBuf<double> x;         // [Nn x Fp]
     DevBuf<double> objective; // [Nn]  f_u(x) + lambda*|x_pen|_1
     int iterations = 0, n_fg = 0, n_f = 0, n_unconverged = 0;
@@ -117,6 +120,9 @@ void build_multibody_features(Histogram& h, int order, const std::vector<int32_t
                               cudaStream_t st);
 // sample-major copy [Kp x Fp] of Q [Fp x Kp] (cached in h.P)
 const int8_t* ensure_P(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st);
+// sample-blocked copy [Kp/128][Fp][128] of Q [Fp x Kp] (cached in h.Qb): every 128-sample tile is contiguous
+const int8_t* ensure_Qb(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st);
+void launch_block_copy(const int8_t* Q, int8_t* Qb, int Fp, int64_t Kp, cudaStream_t st);
 
 // --- newton.cu : fp64 proximal-Newton / barrier-Newton for small feature counts
 constexpr int NEWTON_MAX_F = 64;
@@ -132,6 +138,10 @@ struct EvalBackend {
     // [Nn x Fp] its gradient when want_grad.  lattice() > 0 means x must lie on that grid.
     virtual void eval(const double* x, bool want_grad, double* f_out, double* g_out, cudaStream_t st) = 0;
     virtual double lattice() const { return 0.0; }
+    // optional per-kernel device timing (opts.reserved[0] != 0): out[0] = energy-kernel ms (full passes),
+    // out[1] = gradient-kernel ms, out[2] = energy-kernel ms (objective-only passes), out[3] unused
+    virtual void set_profiling(bool) {}
+    virtual void collect_profile(double* /*out4*/) {}
 };
 EvalBackend* make_backend_cc(const NodeProblem& p, cudaStream_t st);
 EvalBackend* make_backend_tc(const NodeProblem& p, cudaStream_t st);

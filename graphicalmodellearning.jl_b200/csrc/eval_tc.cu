@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -119,7 +120,6 @@ constexpr double X_LATTICE = 1.0 / 16777216.0;   // 2^-24
 constexpr int X_LIMBS = 4;
 constexpr int NODE_TILE1 = 64;                   // nodes per energy tile (4 limbs -> N = 256)
 constexpr int NODE_TILE2 = 128;                  // nodes per gradient tile (M = 128)
-constexpr int QF_MAX = 1 << 20;                  // objective-term grid
 
 __host__ __device__ constexpr int r_qmax(int nR) { return nR == 2 ? 8000 : (nR == 3 ? 1020000 : 130000000); }
 
@@ -129,12 +129,11 @@ __device__ __forceinline__ int balanced_digit(int& q) {   // returns q mod 128 i
     return d;
 }
 
-struct NodeScale { float inv_df, inv_dr; };      // 1/deltaF, 1/deltaR per node (device)
 
 // x [Nn x Fp] (double, on the lattice) -> limb tiles X4 [(tile*4 + limb)*64 + i][Fp] and per-node scales
 __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __restrict__ x, int Nn, int Fp, int form, double wmax,
-                                                           int nR, int8_t* __restrict__ X4, NodeScale* __restrict__ scale,
-                                                           double* __restrict__ delta /* [2*Nn_pad]: dF, dR */, int* __restrict__ flags) {
+                                                           int nR, int8_t* __restrict__ X4, float* __restrict__ inv_dr,
+                                                           double* __restrict__ delta /* [Nn_pad]: deltaR */, int* __restrict__ flags) {
     const int u = blockIdx.x;
     const int tile = u / NODE_TILE1, i = u % NODE_TILE1;
     __shared__ double red[4];
@@ -157,20 +156,11 @@ __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __rest
     __syncthreads();
     if (threadIdx.x == 0) {
         const double B = red[0] + red[1] + red[2] + red[3];   // |t| <= B for every sample
-        double dF, dR;
-        if (form == GML_B200_RPLE) {
-            dF = wmax * (2.0 * B + 0.6931471805599453) * 1.000001 / QF_MAX;
-            dR = 2.0 * wmax * 1.000001 / r_qmax(nR);
-        } else {
-            const double top = wmax * exp(fmin(B, 80.0)) * 1.000001;
-            dF = top / QF_MAX;
-            dR = top / r_qmax(nR);
-        }
-        scale[u].inv_df = (float)(1.0 / dF);
-        scale[u].inv_dr = (float)(1.0 / dR);
-        // the exact reciprocal of what the epilogue multiplies with, so that value = q * delta holds
-        delta[2 * u] = 1.0 / (double)scale[u].inv_df;
-        delta[2 * u + 1] = 1.0 / (double)scale[u].inv_dr;
+        // residual bound: RISE/logRISE  w e^{-t} <= wmax e^B;  RPLE  2 w sigma(-2t) <= 2 wmax
+        const double top = (form == GML_B200_RPLE) ? 2.0 * wmax : wmax * exp(fmin(B, 80.0));
+        const float inv = (float)(r_qmax(nR) / (top * 1.000001));
+        inv_dr[u] = inv;
+        delta[u] = 1.0 / (double)inv;   // exact reciprocal of what the epilogue multiplies with
     }
 }
 
@@ -179,27 +169,45 @@ __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __rest
 // ------------------------------------------------------------------------------------------
 struct EnergyParams {
     int64_t Kp;
-    int Fp, Nn, n_tiles, node_begin_row;   // node tile t covers base rows node_begin_row + 64 t ...
+    int Fp, Fspin, Nn, n_tiles, node_begin_row;   // node tile t covers spin rows node_begin_row + 64 t ... of each [Fspin x 128] block
+    int n_groups;                          // sample ranges; work item = (group, node tile)
     int64_t sample_blocks;                 // Kp / 128
     int64_t r_rows_per_limb;               // Nn_pad2
-    int nR, form;
+    int nR, form, debug_skip_math;
     const float* w32;
-    const NodeScale* scale;
+    const float* inv_dr;                   // [Nn_pad1] 1/deltaR
     double* fsum;                          // [Nn_pad1] objective sums
 };
 
 constexpr int E_STAGES = 3;
+constexpr int E_EPI_WARPS = 8;                       // two per TMEM lane quarter, 32 nodes each
+constexpr int E_THREADS = 64 + 32 * E_EPI_WARPS;
 constexpr int E_A_BYTES = 128 * 128, E_B_BYTES = 256 * 128, E_STAGE_BYTES = E_A_BYTES + E_B_BYTES;
 constexpr int E_S_BYTES = NODE_TILE1 * 128;          // spins tile of the node block
 constexpr int E_R_BYTES_PER_LIMB = NODE_TILE1 * 128; // staging for the R limbs
-constexpr int E_SMEM = E_STAGES * E_STAGE_BYTES + 2 * E_S_BYTES + 4 * E_R_BYTES_PER_LIMB + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int E_SMEM = E_STAGES * E_STAGE_BYTES + 2 * E_S_BYTES + 4 * E_R_BYTES_PER_LIMB + 1024 /*align*/ + 512 /*barriers, scales*/;
 
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Work decomposition: item = (sample range g, node tile nt), ordered group-major and dealt round-robin,
+// so CTAs that run concurrently stream the SAME sample blocks for different node tiles (the P tiles are
+// shared through L2 instead of being re-read from HBM once per node tile), while each CTA keeps one node
+// tile for a whole sample range (objective partial sums stay in registers).
 template <int FORM, bool GRAD>
-__global__ void __launch_bounds__(192, 1) tc_energy_kernel(const __grid_constant__ CUtensorMap tmA,   // P  [Kp x Fp]
-                                                          const __grid_constant__ CUtensorMap tmB,   // X4 [tiles*256 x Fp]
-                                                          const __grid_constant__ CUtensorMap tmS,   // base [Fb x Kp], box 64 rows
-                                                          const __grid_constant__ CUtensorMap tmR,   // R  [nR*Nn_pad2 x Kp], box 64 rows
-                                                          EnergyParams p) {
+__global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_constant__ CUtensorMap tmA,   // P  [Kp x Fp]
+                                                                const __grid_constant__ CUtensorMap tmB,   // X4 [tiles*256 x Fp]
+                                                                const __grid_constant__ CUtensorMap tmS,   // spins, sample-blocked [SB*Fspin x 128], box 64 rows
+                                                                const __grid_constant__ CUtensorMap tmR,   // R  [SB*nR*Nn_pad2 x 128], box 64 rows
+                                                                EnergyParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_stage = smem;
@@ -213,17 +221,18 @@ __global__ void __launch_bounds__(192, 1) tc_energy_kernel(const __grid_constant
     uint64_t* sfull = tempty + 2;             // [2]
     uint64_t* sempty = sfull + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
+    float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);   // [64] 1/deltaR of the node tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = p.Fp / 128;
-    const int64_t total = (int64_t)p.n_tiles * p.sample_blocks;
-    const int64_t per = total / gridDim.x, rem = total % gridDim.x;
-    const int64_t u_begin = (int64_t)blockIdx.x * per + ((int64_t)blockIdx.x < rem ? (int64_t)blockIdx.x : rem);
-    const int64_t u_end = u_begin + per + (blockIdx.x < rem ? 1 : 0);
+    const int n_items = p.n_tiles * p.n_groups;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < E_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 4); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1); mbar_init(&tempty[i], E_EPI_WARPS);
+            mbar_init(&sfull[i], 1); mbar_init(&sempty[i], E_EPI_WARPS);
+        }
         fence_barrier_init();
         prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmS);
         if (GRAD) prefetch_tmap(&tmR);
@@ -234,25 +243,34 @@ __global__ void __launch_bounds__(192, 1) tc_energy_kernel(const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    auto item_range = [&](int item, int& nt, int64_t& b0, int64_t& b1) {
+        const int g = item / p.n_tiles;
+        nt = item % p.n_tiles;
+        b0 = p.sample_blocks * g / p.n_groups;
+        b1 = p.sample_blocks * (g + 1) / p.n_groups;
+    };
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int slot = 0; uint32_t sphase = 0;
-            for (int64_t idx = u_begin; idx < u_end; ++idx) {
-                const int nt = (int)(idx / p.sample_blocks);
-                const int64_t sb = idx % p.sample_blocks;
-                mbar_wait(&sempty[slot], sphase ^ 1);
-                mbar_expect_tx(&sfull[slot], E_S_BYTES);
-                tma_load_2d(s_spin + slot * E_S_BYTES, &tmS, &sfull[slot], (int)(sb * 128), p.node_begin_row + nt * NODE_TILE1);
-                if (++slot == 2) { slot = 0; sphase ^= 1; }
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], E_STAGE_BYTES);
-                    uint8_t* a = s_stage + stage * E_STAGE_BYTES;
-                    tma_load_2d(a, &tmA, &full[stage], kb * 128, (int)(sb * 128));
-                    tma_load_2d(a + E_A_BYTES, &tmB, &full[stage], kb * 128, nt * 256);
-                    if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int nt; int64_t b0, b1;
+                item_range(item, nt, b0, b1);
+                for (int64_t sb = b0; sb < b1; ++sb) {
+                    mbar_wait(&sempty[slot], sphase ^ 1);
+                    mbar_expect_tx(&sfull[slot], E_S_BYTES);
+                    tma_load_2d(s_spin + slot * E_S_BYTES, &tmS, &sfull[slot], 0, (int)(sb * p.Fspin) + p.node_begin_row + nt * NODE_TILE1);
+                    if (++slot == 2) { slot = 0; sphase ^= 1; }
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], E_STAGE_BYTES);
+                        uint8_t* a = s_stage + stage * E_STAGE_BYTES;
+                        tma_load_2d(a, &tmA, &full[stage], kb * 128, (int)(sb * 128));
+                        tma_load_2d(a + E_A_BYTES, &tmB, &full[stage], kb * 128, nt * 256);
+                        if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -262,134 +280,146 @@ __global__ void __launch_bounds__(192, 1) tc_energy_kernel(const __grid_constant
             constexpr uint32_t idesc = make_idesc_i8(128, 256);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int64_t idx = u_begin; idx < u_end; ++idx) {
-                mbar_wait(&tempty[as], aphase ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + as * 256;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int nt; int64_t b0, b1;
+                item_range(item, nt, b0, b1);
+                for (int64_t sb = b0; sb < b1; ++sb) {
+                    mbar_wait(&tempty[as], aphase ^ 1);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(s_stage + stage * E_STAGE_BYTES);
-                    const uint64_t da = make_kmajor_desc(a_addr), db = make_kmajor_desc(a_addr + E_A_BYTES);
+                    const uint32_t d = tmem_base + as * 256;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(s_stage + stage * E_STAGE_BYTES);
+                        const uint64_t da = make_kmajor_desc(a_addr), db = make_kmajor_desc(a_addr + E_A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_i8(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(&empty[stage]);
-                    if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
+                        for (int k = 0; k < 4; ++k) umma_i8(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        umma_commit(&empty[stage]);
+                        if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&tfull[as]);
+                    if (++as == 2) { as = 0; aphase ^= 1; }
                 }
-                umma_commit(&tfull[as]);
-                if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
     } else {
-        // ================= epilogue warps (2..5): TMEM lane quarter = warp % 4 =================
+        // ================= epilogue warps 2..9: TMEM lane quarter = warp % 4, node half = (warp-2)/4 =========
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;            // sample within the block == TMEM lane
-        const int et = threadIdx.x - 64;                // 0..127
-        // objective terms: fp32 per-thread partial sums over at most F_FLUSH sample blocks, then fp64
-        float facc[NODE_TILE1];
-#pragma unroll
-        for (int i = 0; i < NODE_TILE1; ++i) facc[i] = 0.f;
+        const int et = threadIdx.x - 64;                // 0..255
+        constexpr int NPT = NODE_TILE1 / 2;             // nodes per thread
+        constexpr int EPI_THREADS = 32 * E_EPI_WARPS;
+        float facc[NPT];
         int as = 0; uint32_t aphase = 0;
         int slot = 0; uint32_t sphase = 0;
-        int cur_nt = -1, since_flush = 0;
-        auto flush = [&](int nt) {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int nt; int64_t b0, b1;
+            item_range(item, nt, b0, b1);
 #pragma unroll
-            for (int i = 0; i < NODE_TILE1; ++i) {
-                double v = (double)facc[i];
-                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) atomicAdd(p.fsum + (int64_t)nt * NODE_TILE1 + i, v);
-                facc[i] = 0.f;
-            }
-        };
-        for (int64_t idx = u_begin; idx < u_end; ++idx) {
-            const int nt = (int)(idx / p.sample_blocks);
-            const int64_t sb = idx % p.sample_blocks;
-            if (nt != cur_nt || since_flush >= 32) {
-                if (cur_nt >= 0) flush(cur_nt);
-                cur_nt = nt; since_flush = 0;
-            }
-            ++since_flush;
-            const float wk = p.w32[sb * 128 + row];
-            mbar_wait(&sfull[slot], sphase);
-            mbar_wait(&tfull[as], aphase);
-            tc_fence_after();
+            for (int i = 0; i < NPT; ++i) facc[i] = 0.f;
             if (GRAD) {
-                if (et == 0) tma_store_wait_read();   // previous tile's stores have drained the staging buffer
-                named_bar_sync(1, 128);
+                named_bar_sync(1, EPI_THREADS);          // previous item's readers are done with s_scale
+                if (et < NODE_TILE1) s_scale[et] = p.inv_dr[nt * NODE_TILE1 + et];
+                named_bar_sync(1, EPI_THREADS);
             }
-            const uint8_t* spin = s_spin + slot * E_S_BYTES;
-            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256;
+            int since_flush = 0;
+            auto flush = [&]() {
 #pragma unroll
-            for (int c = 0; c < NODE_TILE1 / 16; ++c) {
-                int32_t a0[16], a1[16], a2[16], a3[16];
-                tmem_ld16(tbase + 0 * NODE_TILE1 + c * 16, a0);
-                tmem_ld16(tbase + 1 * NODE_TILE1 + c * 16, a1);
-                tmem_ld16(tbase + 2 * NODE_TILE1 + c * 16, a2);
-                tmem_ld16(tbase + 3 * NODE_TILE1 + c * 16, a3);
-                tmem_ld_wait();
-                if (c == NODE_TILE1 / 16 - 1) {       // accumulator fully read: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[as]);
+                for (int i = 0; i < NPT; ++i) {
+                    double v = (double)facc[i];
+                    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) atomicAdd(p.fsum + (int64_t)nt * NODE_TILE1 + half * NPT + i, v);
+                    facc[i] = 0.f;
                 }
+            };
+            for (int64_t sb = b0; sb < b1; ++sb) {
+                // objective terms: fp32 per-thread partial sums over at most 32 sample blocks, then fp64
+                if (since_flush >= 32) { flush(); since_flush = 0; }
+                ++since_flush;
+                const float wk = p.w32[sb * 128 + row];
+                mbar_wait(&sfull[slot], sphase);
+                mbar_wait(&tfull[as], aphase);
+                tc_fence_after();
+                if (GRAD) {
+                    if (et == 0) tma_store_wait_read();   // previous block's stores have drained the staging buffer
+                    named_bar_sync(1, EPI_THREADS);
+                }
+                const uint8_t* spin = s_spin + slot * E_S_BYTES;
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256 + half * NPT;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int node_in_tile = c * 16 + i;
-                    const int hi = a0[i] * 128 + a1[i], lo = a2[i] * 128 + a3[i];
-                    const float e = fmaf((float)hi, 16384.f, (float)lo) * (float)X_LATTICE;
-                    const float su = (float)(int8_t)spin[node_in_tile * 128 + row];
-                    const float t = su * e;
-                    const NodeScale sc = p.scale[nt * NODE_TILE1 + node_in_tile];
-                    float fterm, gterm;
-                    if (FORM == GML_B200_RPLE) {
-                        const float a = -2.f * t;
-                        const float ex = exp2f(-fabsf(a) * 1.4426950408889634f);
-                        fterm = wk * (fmaxf(a, 0.f) + log1pf(ex));
-                        gterm = 2.f * wk * (a > 0.f ? 1.f : ex) / (1.f + ex);       // 2 w sigma(-2t)
-                    } else {
-                        const float psi = exp2f(fminf(-t, 80.f) * 1.4426950408889634f);
-                        fterm = wk * psi; gterm = fterm;
+                for (int c = 0; c < NPT / 16; ++c) {
+                    int32_t a0[16], a1[16], a2[16], a3[16];
+                    tmem_ld16(tbase + 0 * NODE_TILE1 + c * 16, a0);
+                    tmem_ld16(tbase + 1 * NODE_TILE1 + c * 16, a1);
+                    tmem_ld16(tbase + 2 * NODE_TILE1 + c * 16, a2);
+                    tmem_ld16(tbase + 3 * NODE_TILE1 + c * 16, a3);
+                    tmem_ld_wait();
+                    if (c == NPT / 16 - 1) {              // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[as]);
                     }
-                    facc[node_in_tile] += fterm;
-                    if (GRAD) {
-                        int q = __float2int_rn(su * gterm * sc.inv_dr);
-                        const int d_lo = balanced_digit(q);
-                        if (p.nR == 2) {
-                            s_r[(0 * NODE_TILE1 + node_in_tile) * 128 + row] = (uint8_t)(int8_t)q;
-                            s_r[(1 * NODE_TILE1 + node_in_tile) * 128 + row] = (uint8_t)(int8_t)d_lo;
+                    if (p.debug_skip_math) { facc[c] += (float)(a0[0] + a1[1] + a2[2] + a3[3]); continue; }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int node_in_tile = half * NPT + c * 16 + i;
+                        const int hi = a0[i] * 128 + a1[i], lo = a2[i] * 128 + a3[i];
+                        const float e = fmaf((float)hi, 16384.f, (float)lo) * (float)X_LATTICE;
+                        const float su = (float)(int8_t)spin[node_in_tile * 128 + row];
+                        const float t = su * e;
+                        float fterm, gterm;
+                        if (FORM == GML_B200_RPLE) {
+                            const float a = -2.f * t;
+                            const float ex = fast_ex2(-fabsf(a) * 1.4426950408889634f);
+                            fterm = wk * fmaf(fast_lg2(1.f + ex), 0.6931471805599453f, fmaxf(a, 0.f));
+                            gterm = __fdividef(2.f * wk * (a > 0.f ? 1.f : ex), 1.f + ex);   // 2 w sigma(-2t)
                         } else {
-                            const int d_mid = balanced_digit(q);
-                            if (p.nR == 3) {
-                                s_r[(0 * NODE_TILE1 + node_in_tile) * 128 + row] = (uint8_t)(int8_t)q;
-                                s_r[(1 * NODE_TILE1 + node_in_tile) * 128 + row] = (uint8_t)(int8_t)d_mid;
-                                s_r[(2 * NODE_TILE1 + node_in_tile) * 128 + row] = (uint8_t)(int8_t)d_lo;
+                            fterm = wk * fast_ex2(fminf(-t, 80.f) * 1.4426950408889634f);
+                            gterm = fterm;
+                        }
+                        facc[c * 16 + i] += fterm;
+                        if (GRAD) {
+                            int q = __float2int_rn(su * gterm * s_scale[node_in_tile]);
+                            uint8_t* dst = s_r + node_in_tile * 128 + row;
+                            const int d_lo = balanced_digit(q);
+                            if (p.nR == 2) {
+                                dst[0 * E_R_BYTES_PER_LIMB] = (uint8_t)q;
+                                dst[1 * E_R_BYTES_PER_LIMB] = (uint8_t)d_lo;
                             } else {
-                                const int d_2 = balanced_digit(q);
-                                s_r[(0 * NODE_TILE1 + node_in_tile) * 128 + row] = (uint8_t)(int8_t)q;
-                                s_r[(1 * NODE_TILE1 + node_in_tile) * 128 + row] = (uint8_t)(int8_t)d_2;
-                                s_r[(2 * NODE_TILE1 + node_in_tile) * 128 + row] = (uint8_t)(int8_t)d_mid;
-                                s_r[(3 * NODE_TILE1 + node_in_tile) * 128 + row] = (uint8_t)(int8_t)d_lo;
+                                const int d_mid = balanced_digit(q);
+                                if (p.nR == 3) {
+                                    dst[0 * E_R_BYTES_PER_LIMB] = (uint8_t)q;
+                                    dst[1 * E_R_BYTES_PER_LIMB] = (uint8_t)d_mid;
+                                    dst[2 * E_R_BYTES_PER_LIMB] = (uint8_t)d_lo;
+                                } else {
+                                    const int d_2 = balanced_digit(q);
+                                    dst[0 * E_R_BYTES_PER_LIMB] = (uint8_t)q;
+                                    dst[1 * E_R_BYTES_PER_LIMB] = (uint8_t)d_2;
+                                    dst[2 * E_R_BYTES_PER_LIMB] = (uint8_t)d_mid;
+                                    dst[3 * E_R_BYTES_PER_LIMB] = (uint8_t)d_lo;
+                                }
                             }
                         }
                     }
                 }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sempty[slot]);
-            if (GRAD) {
-                fence_proxy_async();
-                named_bar_sync(1, 128);
-                if (et == 0) {
-                    for (int j = 0; j < p.nR; ++j)
-                        tma_store_2d(&tmR, s_r + j * E_R_BYTES_PER_LIMB, (int)(sb * 128),
-                                     (int)(j * p.r_rows_per_limb) + nt * NODE_TILE1);
-                    tma_store_commit();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sempty[slot]);
+                if (GRAD) {
+                    fence_proxy_async();
+                    named_bar_sync(1, EPI_THREADS);
+                    if (et == 0) {
+                        for (int j = 0; j < p.nR; ++j)
+                            tma_store_2d(&tmR, s_r + j * E_R_BYTES_PER_LIMB, 0,
+                                         (int)((sb * p.nR + j) * p.r_rows_per_limb) + nt * NODE_TILE1);
+                        tma_store_commit();
+                    }
                 }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+                if (++slot == 2) { slot = 0; sphase ^= 1; }
             }
-            if (++as == 2) { as = 0; aphase ^= 1; }
-            if (++slot == 2) { slot = 0; sphase ^= 1; }
+            flush();
         }
-        if (cur_nt >= 0) flush(cur_nt);
         if (GRAD && et == 0) tma_store_wait_all();
     }
     tc_fence_before();
@@ -403,16 +433,21 @@ __global__ void __launch_bounds__(192, 1) tc_energy_kernel(const __grid_constant
 struct GradParams {
     int Fp, m_tiles, f_tiles, nR;
     int64_t r_rows_per_limb;      // Nn_pad2
-    int64_t chunks, chunk_blocks, sample_blocks;
+    int n_splits;                 // sample ranges; work item = (split, output tile)
+    int64_t sample_blocks;
     long long* G;                 // [Nn_pad2 x Fp] int64
 };
 
 constexpr int G_TILE_BYTES = 128 * 128;
+constexpr int64_t G_MAX_BLOCKS = 1 << 16;   // int32 accumulators: |acc| <= 64 * 128 * blocks < 2^31
 __host__ __device__ constexpr int g_stages(int nr) { return nr >= 4 ? 2 : 3; }
 
+// Work decomposition: item = (sample split ks, output tile), split-major and dealt round-robin, one item
+// per CTA when tiles * splits <= #SMs.  All CTAs of a split then sweep the SAME sample blocks in lockstep
+// for different output tiles, so every R / Q operand tile is fetched from HBM once and shared through L2.
 template <int NR>
-__global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__ CUtensorMap tmRa,   // R [nR*Nn_pad2 x Kp], box 128 rows, SW128
-                                                        const __grid_constant__ CUtensorMap tmQ,    // Q [Fp x Kp], box 128 rows, SW128
+__global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__ CUtensorMap tmRa,   // R  [SB*nR*Nn_pad2 x 128], box 128 rows, SW128
+                                                        const __grid_constant__ CUtensorMap tmQ,    // Qb [SB*Fp x 128], box 128 rows, SW128
                                                         GradParams p) {
     constexpr int STAGE_BYTES = (NR + 1) * G_TILE_BYTES;
     constexpr int G_STAGES = g_stages(NR);
@@ -426,11 +461,8 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int64_t tiles = (int64_t)p.m_tiles * p.f_tiles;
-    const int64_t total = tiles * p.chunks;
-    const int64_t per = total / gridDim.x, rem = total % gridDim.x;
-    const int64_t u_begin = (int64_t)blockIdx.x * per + ((int64_t)blockIdx.x < rem ? (int64_t)blockIdx.x : rem);
-    const int64_t u_end = u_begin + per + (blockIdx.x < rem ? 1 : 0);
+    const int tiles = p.m_tiles * p.f_tiles;
+    const int n_items = tiles * p.n_splits;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < G_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -444,28 +476,27 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // unit -> (chunk, m tile, f tile); chunk-major so that concurrently running CTAs share operand tiles in L2
-    auto decode = [&](int64_t idx, int64_t& chunk, int& mt, int& ft) {
-        chunk = idx / tiles;
-        const int r = (int)(idx % tiles);
+    auto decode = [&](int item, int& mt, int& ft, int64_t& b0, int64_t& b1) {
+        const int ks = item / tiles, r = item % tiles;
         mt = r / p.f_tiles; ft = r % p.f_tiles;
+        b0 = p.sample_blocks * ks / p.n_splits;
+        b1 = p.sample_blocks * (ks + 1) / p.n_splits;
     };
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t idx = u_begin; idx < u_end; ++idx) {
-                int64_t chunk; int mt, ft;
-                decode(idx, chunk, mt, ft);
-                const int64_t b0 = chunk * p.chunk_blocks, b1 = min(b0 + p.chunk_blocks, p.sample_blocks);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int mt, ft; int64_t b0, b1;
+                decode(item, mt, ft, b0, b1);
                 for (int64_t b = b0; b < b1; ++b) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     uint8_t* s = smem + stage * STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < NR; ++j)
-                        tma_load_2d(s + j * G_TILE_BYTES, &tmRa, &full[stage], (int)(b * 128), (int)(j * p.r_rows_per_limb) + mt * 128);
-                    tma_load_2d(s + NR * G_TILE_BYTES, &tmQ, &full[stage], (int)(b * 128), ft * 128);
+                        tma_load_2d(s + j * G_TILE_BYTES, &tmRa, &full[stage], 0, (int)((b * NR + j) * p.r_rows_per_limb) + mt * 128);
+                    tma_load_2d(s + NR * G_TILE_BYTES, &tmQ, &full[stage], 0, (int)(b * p.Fp) + ft * 128);
                     if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -474,59 +505,63 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_i8(128, 128);
             int stage = 0; uint32_t phase = 0, aphase = 0;
-            for (int64_t idx = u_begin; idx < u_end; ++idx) {
-                int64_t chunk; int mt, ft;
-                decode(idx, chunk, mt, ft);
-                const int64_t b0 = chunk * p.chunk_blocks, b1 = min(b0 + p.chunk_blocks, p.sample_blocks);
-                mbar_wait(tempty, aphase ^ 1);
-                tc_fence_after();
-                for (int64_t b = b0; b < b1; ++b) {
-                    mbar_wait(&full[stage], phase);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int mt, ft; int64_t b0, b1;
+                decode(item, mt, ft, b0, b1);
+                for (int64_t c0 = b0; c0 < b1; c0 += G_MAX_BLOCKS) {       // sub-chunks bounded by the int32 range
+                    const int64_t c1 = min(c0 + G_MAX_BLOCKS, b1);
+                    mbar_wait(tempty, aphase ^ 1);
                     tc_fence_after();
-                    const uint32_t s_addr = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t db = make_kmajor_desc(s_addr + NR * G_TILE_BYTES);
+                    for (int64_t b = c0; b < c1; ++b) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t s_addr = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t db = make_kmajor_desc(s_addr + NR * G_TILE_BYTES);
 #pragma unroll
-                    for (int j = 0; j < NR; ++j) {
-                        const uint64_t da = make_kmajor_desc(s_addr + j * G_TILE_BYTES);
+                        for (int j = 0; j < NR; ++j) {
+                            const uint64_t da = make_kmajor_desc(s_addr + j * G_TILE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_i8(tmem_base + j * 128, da + 2 * k, db + 2 * k, idesc, (b > b0 || k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) umma_i8(tmem_base + j * 128, da + 2 * k, db + 2 * k, idesc, (b > c0 || k) ? 1u : 0u);
+                        }
+                        umma_commit(&empty[stage]);
+                        if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty[stage]);
-                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(tfull);
+                    aphase ^= 1;
                 }
-                umma_commit(tfull);
-                aphase ^= 1;
             }
         }
     } else {
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         uint32_t aphase = 0;
-        for (int64_t idx = u_begin; idx < u_end; ++idx) {
-            int64_t chunk; int mt, ft;
-            decode(idx, chunk, mt, ft);
-            mbar_wait(tfull, aphase);
-            tc_fence_after();
-            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
-            long long* dst = p.G + ((int64_t)mt * 128 + row) * p.Fp + ft * 128;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int mt, ft; int64_t b0, b1;
+            decode(item, mt, ft, b0, b1);
+            for (int64_t c0 = b0; c0 < b1; c0 += G_MAX_BLOCKS) {
+                mbar_wait(tfull, aphase);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
+                long long* dst = p.G + ((int64_t)mt * 128 + row) * p.Fp + ft * 128;
 #pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
-                int32_t acc[NR][16];
+                for (int c = 0; c < 8; ++c) {
+                    int32_t acc[NR][16];
 #pragma unroll
-                for (int j = 0; j < NR; ++j) tmem_ld16(tbase + j * 128 + c * 16, acc[j]);
-                tmem_ld_wait();
+                    for (int j = 0; j < NR; ++j) tmem_ld16(tbase + j * 128 + c * 16, acc[j]);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    long long v = 0;
+                    for (int i = 0; i < 16; ++i) {
+                        long long v = 0;
 #pragma unroll
-                    for (int j = 0; j < NR; ++j) v = v * 128 + (long long)acc[j][i];
-                    if (v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst + c * 16 + i), (unsigned long long)v);
+                        for (int j = 0; j < NR; ++j) v = v * 128 + (long long)acc[j][i];
+                        if (v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst + c * 16 + i), (unsigned long long)v);
+                    }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty);
+                aphase ^= 1;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty);
-            aphase ^= 1;
         }
     }
     tc_fence_before();
@@ -542,7 +577,7 @@ __global__ void tc_finalize_kernel(int form, int Nn, int Fp, const double* __res
     const double fs = fsum[u];
     if (threadIdx.x == 0) f_out[u] = (form == GML_B200_LOGRISE) ? log(fs) : fs;
     if (!want_grad) return;
-    const double sc = -delta[2 * u + 1] / (form == GML_B200_LOGRISE ? fs : 1.0);
+    const double sc = -delta[u] / (form == GML_B200_LOGRISE ? fs : 1.0);
     for (int f = threadIdx.x; f < Fp; f += blockDim.x) g_out[(int64_t)u * Fp + f] = sc * (double)G64[(int64_t)u * Fp + f];
 }
 
@@ -584,12 +619,16 @@ struct BackendTC : EvalBackend {
     int Nn_pad1, Nn_pad2, nR, n_sms;
     int32_t first_row = 0;   // spin rows of this shard are contiguous in `base`: spin_row[u] = first_row + u
     DevBuf<int8_t> X4, R;
-    DevBuf<NodeScale> scale;
+    DevBuf<float> inv_dr;
     DevBuf<double> delta;
     DevBuf<double> fsum;
     DevBuf<long long> G64;
     DevBuf<int> flags;
     const int8_t* P;
+    const int8_t* Qb;
+    const int8_t* spin_blocked = nullptr;
+    int Fspin = 0;
+    DevBuf<int8_t> base_blocked;
     CUtensorMap tmA, tmB, tmS, tmR, tmRa, tmQ;
 
     BackendTC(const NodeProblem& prob, cudaStream_t st) : p(prob) {
@@ -605,7 +644,7 @@ struct BackendTC : EvalBackend {
         P = ensure_P(h, p.Q, p.Fp, st);
         X4.alloc((size_t)Nn_pad1 * X_LIMBS * p.Fp);
         R.alloc((size_t)nR * Nn_pad2 * h.Kp);
-        scale.alloc(Nn_pad1); delta.alloc(2 * (size_t)Nn_pad1);
+        inv_dr.alloc(Nn_pad1); delta.alloc(Nn_pad1);
         fsum.alloc(Nn_pad1);
         G64.alloc((size_t)Nn_pad2 * p.Fp);
         flags.alloc(1);
@@ -614,10 +653,24 @@ struct BackendTC : EvalBackend {
         GML_CUDA(cudaMemsetAsync(R.p, 0, (size_t)nR * Nn_pad2 * h.Kp, st));
         tmA = make_map_2d(P, p.Fp, h.Kp, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         tmB = make_map_2d(X4.p, p.Fp, (uint64_t)Nn_pad1 * X_LIMBS, 128, 256, CU_TENSOR_MAP_SWIZZLE_128B);
-        tmS = make_map_2d(h.base.p, h.Kp, h.Fb, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
-        tmR = make_map_2d(R.p, h.Kp, (uint64_t)nR * Nn_pad2, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
-        tmRa = make_map_2d(R.p, h.Kp, (uint64_t)nR * Nn_pad2, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-        tmQ = make_map_2d(p.Q, h.Kp, p.Fp, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+        // Sample-blocked layouts: every TMA box is one contiguous 8/16 KB chunk (one 2 MB page) instead of
+        // 64/128 rows that are Kp bytes apart.
+        const uint64_t SB = (uint64_t)(h.Kp / 128);
+        GML_REQUIRE(SB * nR * Nn_pad2 < (1ull << 31) && SB * h.Fb < (1ull << 31) && SB * p.Fp < (1ull << 31),
+                    "problem too large for 32-bit TMA row coordinates: shard the nodes or the samples");
+        Qb = ensure_Qb(h, p.Q, p.Fp, st);
+        // spins of the shard's nodes: for pairwise problems they are rows of Q itself; multibody problems
+        // read them from the blocked copy of `base` (built on demand)
+        if (p.Q == h.base.p) { spin_blocked = Qb; Fspin = p.Fp; }
+        else {
+            base_blocked.alloc((size_t)h.Kp * h.Fb);
+            launch_block_copy(h.base.p, base_blocked.p, h.Fb, h.Kp, st);
+            spin_blocked = base_blocked.p; Fspin = h.Fb;
+        }
+        tmS = make_map_2d(spin_blocked, 128, SB * Fspin, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
+        tmR = make_map_2d(R.p, 128, SB * nR * Nn_pad2, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
+        tmRa = make_map_2d(R.p, 128, SB * nR * Nn_pad2, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+        tmQ = make_map_2d(Qb, 128, SB * p.Fp, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         GML_CUDA(cudaMemcpyAsync(&first_row, p.spin_row.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         GML_CUDA(cudaStreamSynchronize(st));
         configure();
@@ -638,43 +691,68 @@ struct BackendTC : EvalBackend {
 
     double lattice() const override { return X_LATTICE; }
 
+    // ---- per-kernel timing with CUDA events on the launch stream
+    bool profiling = false;
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;
+    void set_profiling(bool on) override { profiling = on; }
+    void span_begin(int kind, cudaStream_t st) {
+        if (!profiling) return;
+        Span s; s.kind = kind;
+        GML_CUDA(cudaEventCreate(&s.a)); GML_CUDA(cudaEventCreate(&s.b));
+        GML_CUDA(cudaEventRecord(s.a, st));
+        spans.push_back(s);
+    }
+    void span_end(cudaStream_t st) { if (profiling) GML_CUDA(cudaEventRecord(spans.back().b, st)); }
+    void collect_profile(double* out) override {
+        for (auto& s : spans) {
+            float ms = 0.f;
+            GML_CUDA(cudaEventSynchronize(s.b));
+            GML_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+            out[s.kind] += ms;
+            cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+        }
+        spans.clear();
+    }
+    ~BackendTC() override { for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); } }
+
     void eval(const double* x, bool want_grad, double* f_out, double* g_out, cudaStream_t st) override {
         const Histogram& h = *p.hist;
-        tc_quantize_x_kernel<<<Nn_pad1, 128, 0, st>>>(x, p.Nn, p.Fp, p.form, h.wmax, nR, X4.p, scale.p, delta.p, flags.p);
+        tc_quantize_x_kernel<<<Nn_pad1, 128, 0, st>>>(x, p.Nn, p.Fp, p.form, h.wmax, nR, X4.p, inv_dr.p, delta.p, flags.p);
         GML_LAUNCHED();
         GML_CUDA(cudaMemsetAsync(fsum.p, 0, sizeof(double) * Nn_pad1, st));
         EnergyParams ep{};
-        ep.Kp = h.Kp; ep.Fp = p.Fp; ep.Nn = p.Nn; ep.n_tiles = Nn_pad1 / NODE_TILE1;
+        ep.Kp = h.Kp; ep.Fp = p.Fp; ep.Fspin = Fspin; ep.Nn = p.Nn; ep.n_tiles = Nn_pad1 / NODE_TILE1;
         ep.sample_blocks = h.Kp / 128; ep.r_rows_per_limb = Nn_pad2; ep.nR = nR; ep.form = p.form;
-        ep.w32 = h.w32.p; ep.scale = scale.p; ep.fsum = fsum.p;
+        ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p;
+        ep.debug_skip_math = std::getenv("GML_TC_DEBUG_SKIP_MATH") ? 1 : 0;
         ep.node_begin_row = first_row;
-        const int64_t units = (int64_t)ep.n_tiles * ep.sample_blocks;
-        const int grid1 = (int)std::min<int64_t>(units, n_sms);
+        ep.n_groups = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / ep.n_tiles, ep.sample_blocks));
+        const int grid1 = std::min(n_sms, ep.n_tiles * ep.n_groups);
         const bool rple = p.form == GML_B200_RPLE;
+        span_begin(want_grad ? 0 : 2, st);
         if (want_grad) {
-            if (rple) tc_energy_kernel<GML_B200_RPLE, true><<<grid1, 192, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
-            else tc_energy_kernel<GML_B200_RISE, true><<<grid1, 192, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
+            if (rple) tc_energy_kernel<GML_B200_RPLE, true><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
+            else tc_energy_kernel<GML_B200_RISE, true><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
         } else {
-            if (rple) tc_energy_kernel<GML_B200_RPLE, false><<<grid1, 192, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
-            else tc_energy_kernel<GML_B200_RISE, false><<<grid1, 192, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
+            if (rple) tc_energy_kernel<GML_B200_RPLE, false><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
+            else tc_energy_kernel<GML_B200_RISE, false><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
         }
         GML_LAUNCHED();
+        span_end(st);
         if (want_grad) {
             GML_CUDA(cudaMemsetAsync(G64.p, 0, sizeof(long long) * Nn_pad2 * p.Fp, st));
             GradParams gp{};
             gp.Fp = p.Fp; gp.m_tiles = Nn_pad2 / 128; gp.f_tiles = p.Fp / 128; gp.nR = nR;
             gp.r_rows_per_limb = Nn_pad2; gp.sample_blocks = h.Kp / 128; gp.G = G64.p;
-            const int64_t tiles = (int64_t)gp.m_tiles * gp.f_tiles;
-            // split the sample axis so that there are ~4 units per SM, at most 2^17 samples per unit
-            int64_t chunks = std::max<int64_t>(1, ceil_div((int64_t)n_sms * 4, tiles));
-            chunks = std::min<int64_t>(chunks, gp.sample_blocks);
-            chunks = std::max<int64_t>(chunks, ceil_div(gp.sample_blocks, 1024));
-            gp.chunk_blocks = ceil_div(gp.sample_blocks, chunks);
-            gp.chunks = ceil_div(gp.sample_blocks, gp.chunk_blocks);
-            const int grid2 = (int)std::min<int64_t>(tiles * gp.chunks, n_sms);
+            const int tiles = gp.m_tiles * gp.f_tiles;
+            gp.n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / tiles, gp.sample_blocks));
+            const int grid2 = std::min(n_sms, tiles * gp.n_splits);
+            span_begin(1, st);
             if (nR == 3) tc_grad_kernel<3><<<grid2, 192, grad_smem(3), st>>>(tmRa, tmQ, gp);
             else tc_grad_kernel<4><<<grid2, 192, grad_smem(4), st>>>(tmRa, tmQ, gp);
             GML_LAUNCHED();
+            span_end(st);
         }
         tc_finalize_kernel<<<p.Nn, 128, 0, st>>>(p.form, p.Nn, p.Fp, fsum.p, G64.p, delta.p, f_out, g_out, want_grad ? 1 : 0);
         GML_LAUNCHED();

@@ -153,6 +153,7 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     const int Nn = prob.Nn, Fp = prob.Fp;
     std::unique_ptr<EvalBackend> be(backend == GML_B200_SOLVER_FISTA_TC ? make_backend_tc(prob, st)
                                                                         : make_backend_cc(prob, st));
+    be->set_profiling(o.reserved[0] != 0);
     const size_t nx = (size_t)Nn * Fp;
     DevBuf<double> Z, Y, G, fY, fZ, fX, L, t, q, c, gmap, best;
     DevBuf<int> status, n_active, stall, streak;
@@ -215,6 +216,7 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     double mr = 0.0; int unconv = 0;
     // a node stalled at the gradient noise floor counts as converged when it is within 10x tol
     for (int u = 0; u < Nn; ++u) { mr = std::max(mr, hg[u]); unconv += (hs[u] == 1 || (hs[u] == 2 && hg[u] <= 10.0 * s.tol)) ? 0 : 1; }
+    be->collect_profile(r.profile);
     r.iterations = it; r.n_fg = n_fg; r.n_f = n_f; r.n_unconverged = unconv; r.max_residual = mr;
 }
 

@@ -96,6 +96,17 @@ __global__ void transpose_i8_kernel(const int8_t* __restrict__ Q, int8_t* __rest
     }
 }
 
+// Q [Fp x Kp] -> Qb [Kp/128][Fp][128]: 16 bytes per thread, both sides coalesced in 128 B segments
+__global__ void block_i8_kernel(const int8_t* __restrict__ Q, int8_t* __restrict__ Qb, int Fp, int64_t Kp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 16-byte chunk index
+    const int64_t chunks_per_row = Kp / 16;
+    if (i >= chunks_per_row * Fp) return;
+    const int64_t f = i / chunks_per_row, c = i % chunks_per_row;       // chunk c of feature row f
+    const int64_t sb = c / 8, within = c % 8;
+    const int4 v = *reinterpret_cast<const int4*>(Q + f * Kp + c * 16);
+    *reinterpret_cast<int4*>(Qb + ((sb * Fp + f) * 128) + within * 16) = v;
+}
+
 // multibody base features: row f = product of the spins listed in subsets[f*(order-1) ...]
 __global__ void multibody_features_kernel(const int8_t* __restrict__ base, int64_t Kp, const int32_t* __restrict__ subsets,
                                           int width, int F, int8_t* __restrict__ out) {
@@ -135,7 +146,7 @@ void hist_from_device(Histogram& h, const double* d_counts, const int8_t* d_spin
     h.base.alloc((size_t)h.Fb * h.Kp);
     h.w64.alloc(h.Kp);
     h.w32.alloc(h.Kp);
-    h.mb_order = 0; h.P_of = nullptr;
+    h.mb_order = 0; h.P_of = nullptr; h.Qb_of = nullptr;
 
     DevBuf<double> scal;   // [0] sum, [1] max
     DevBuf<int> flags;
@@ -177,6 +188,7 @@ void build_multibody_features(Histogram& h, int order, const std::vector<int32_t
     GML_LAUNCHED();
     GML_CUDA(cudaStreamSynchronize(st));   // `sub` is freed on return
     if (h.P_of == h.mb.p) h.P_of = nullptr;
+    if (h.Qb_of == h.mb.p) h.Qb_of = nullptr;
 }
 
 const int8_t* ensure_P(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st) {
@@ -187,6 +199,20 @@ const int8_t* ensure_P(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st) {
     GML_LAUNCHED();
     h.P_of = Q;
     return h.P.p;
+}
+
+void launch_block_copy(const int8_t* Q, int8_t* Qb, int Fp, int64_t Kp, cudaStream_t st) {
+    const int64_t chunks = Kp / 16 * Fp;
+    block_i8_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(Q, Qb, Fp, Kp);
+    GML_LAUNCHED();
+}
+
+const int8_t* ensure_Qb(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st) {
+    if (h.Qb_of == Q && h.Qb.p) return h.Qb.p;
+    h.Qb.alloc((size_t)h.Kp * Fp);
+    launch_block_copy(Q, h.Qb.p, Fp, h.Kp, st);
+    h.Qb_of = Q;
+    return h.Qb.p;
 }
 
 }  // namespace gml

@@ -1,0 +1,55 @@
+"""Multi-GPU plumbing: node subproblems are independent (the reference's serial loop at
+src/GraphicalModelLearning.jl:161 has no cross-iteration dependency), so ranks own contiguous node
+shards, the histogram is replicated, and the only exchange is ONE all-gather of the learned rows
+before the symmetrisation (:184-186).  One process per GPU, torch.distributed for the collective."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_nodes: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous balanced shard [begin, end) of rank; the first n_nodes % world ranks get one extra."""
+    base, extra = divmod(n_nodes, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def gather_rows(local_rows: torch.Tensor, n_nodes: int, group=None) -> torch.Tensor:
+    """All-gather the (n_local x N) row blocks into the full N x N row-major matrix on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local_rows
+    n_cols = local_rows.shape[1]
+    max_rows = -(-n_nodes // world)
+    padded = torch.zeros((max_rows, n_cols), dtype=local_rows.dtype, device=local_rows.device)
+    padded[: local_rows.shape[0]] = local_rows
+    out = torch.empty((world * max_rows, n_cols), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    blocks = []
+    for r in range(world):
+        b, e = shard_bounds(n_nodes, world, r)
+        blocks.append(out[r * max_rows: r * max_rows + (e - b)])
+    return torch.cat(blocks, dim=0)
+
+
+def learn_sharded(session, formulation, method, symmetrize: bool = True, group=None) -> torch.Tensor:
+    """learn() for a pairwise formulation with the node loop sharded over the ranks of `group`.
+    `session` holds the (replicated) histogram on this rank's GPU.  Returns the N x N device matrix
+    (row-major, row u = node u) on every rank."""
+    from . import _lib
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = session.N
+    b, e = shard_bounds(n, world, rank)
+    rows = torch.empty((e - b, n), dtype=torch.float64, device=f"cuda:{session.device}")
+    stream = torch.cuda.current_stream().cuda_stream
+    session.solve_pairwise_device(formulation, method, rows.data_ptr(), b, e, stream=stream)
+    full = gather_rows(rows, n, group).contiguous()
+    if symmetrize:
+        import ctypes
+        _lib.check(_lib.load().gml_b200_symmetrize_device(ctypes.c_void_p(full.data_ptr()), n,
+                                                          ctypes.c_void_p(stream)))
+    return full

@@ -55,7 +55,7 @@ typedef struct gml_b200_opts {
     int32_t node_end;
     int32_t verbose;
     void* stream;       /* cudaStream_t to launch on; NULL = the handle's own stream */
-    int32_t reserved[8];
+    int32_t reserved[8]; /* reserved[0] != 0: time the contraction kernels with CUDA events (stats.reserved_d) */
 } gml_b200_opts;
 
 typedef struct gml_b200_stats {
@@ -73,7 +73,8 @@ typedef struct gml_b200_stats {
     double d2h_ms;
     double total_ms;          /* host wall clock of the whole call */
     double max_residual;      /* largest final stopping residual over nodes */
-    double reserved_d[4];
+    double reserved_d[4];     /* profiling: [0] energy kernel ms in full passes, [1] gradient kernel ms,
+                                 [2] energy kernel ms in objective-only passes */
 } gml_b200_stats;
 
 typedef struct gml_b200_handle gml_b200_handle;
@@ -139,6 +140,13 @@ int gml_b200_solve_multibody(gml_b200_handle* h, int32_t interaction_order, doub
  * selects the contraction backend (GML_B200_SOLVER_FISTA_CC or _TC; the TC backend rounds x to its 2^-24 lattice). */
 int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b200_opts* opts, const double* x,
                            double* f_out, double* g_out /* nullable */);
+
+/* Times `reps` full objective+gradient passes and `reps` objective-only passes of the contraction backend
+ * selected by opts->solver over the shard, with CUDA events around each kernel.  out_ms[0] = mean energy-kernel ms
+ * in a full pass, out_ms[1] = mean gradient-kernel ms, out_ms[2] = mean energy-kernel ms in an objective-only
+ * pass, out_ms[3] = mean wall ms of a full pass (all kernels of the pass). */
+int gml_b200_bench_passes(gml_b200_handle* h, int32_t formulation, const gml_b200_opts* opts, int32_t reps,
+                          double* out_ms);
 
 /* 0.5*(R + R') in place on a ROW-major N x N device matrix (src/GraphicalModelLearning.jl:184-186). */
 int gml_b200_symmetrize_device(double* d_theta, int32_t N, void* stream);

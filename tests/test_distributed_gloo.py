@@ -1,0 +1,66 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the shard partition + row all-gather
+(the only exchange of the node-sharded path), checked against the oracle's full matrix."""
+import os
+import pathlib
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def _worker(rank, world, port, samples, expected, result_q):
+    for p in (ROOT, ROOT / "oracle"):
+        sys.path.insert(0, str(p))
+    import c_oracle as c
+    import gml_b200  # noqa: F401
+    from gml_b200.distributed import gather_rows, shard_bounds
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = samples.shape[1] - 1
+    b, e = shard_bounds(n, world, rank)
+    # the shard's rows (what gml_b200_solve_pairwise_device leaves on the GPU), here from the oracle
+    rows = c.learn_pairwise(samples, "RISE", 0.3, False, nodes=(b, e))[b:e]
+    full = gather_rows(torch.from_numpy(np.ascontiguousarray(rows)), n)
+    sym = 0.5 * (full + full.T)
+    result_q.put((rank, float(np.abs(sym.numpy() - expected).max()), tuple(full.shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_all_nodes():
+    sys.path.insert(0, str(ROOT))
+    import gml_b200  # noqa: F401
+    from gml_b200.distributed import shard_bounds
+    for n in (1, 3, 7, 16, 125, 1000):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_bounds(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gather_matches_oracle():
+    for p in (ROOT, ROOT / "oracle", ROOT / "tests"):
+        sys.path.insert(0, str(p))
+    import c_oracle as c
+    from helpers import histogram_c1
+    _, samples = histogram_c1(n=7, m_samples=4000, seed=11)     # 7 nodes over 2 ranks: ragged shards 4 + 3
+    expected = c.learn_pairwise(samples, "RISE", 0.3, True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, samples, expected, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, shape in results:
+        assert shape == (7, 7)
+        assert err <= 1e-12
