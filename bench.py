@@ -200,7 +200,7 @@ def run_b200(args):
     sess = gml_b200.Session(local).attach_device(counts.data_ptr(), spins.data_ptr(), k, n, k)
     form = gml_b200.RISE(0.4, True)
     lam = gml_b200.regularizer_lambda(0.4, n, float(k))
-    method = gml_b200.B200(solver=args.solver, tol=args.tol, device=local, profile=True)
+    method = gml_b200.B200(solver=args.solver, tol=args.tol, device=local, profile=True, verbose=args.verbose)
     b, e = shard_bounds(n, world, rank)
 
     def barrier():
@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-rows", type=int, default=2048)
     ap.add_argument("--cpu-nodes-per-core", type=int, default=1)
+    ap.add_argument("--verbose", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,15 +1,22 @@
 // K4: batched FISTA driver.  All Nn node problems advance together; every node carries its own
 // Lipschitz estimate L_u, momentum t_u, restart and convergence state, so there is no host decision
-// inside a round:
-//     trial   Z_u = prox_{lambda/L_u}(Y_u - G_u/L_u)            (soft-threshold on PEN_L1 coordinates)
-//     f(Z)    one objective-only pass over the histogram
-//     accept  sufficient decrease f(Z) <= f(Y) + <G,Z-Y> + L/2|Z-Y|^2 ?  yes: momentum/restart/
-//             convergence, no: L_u *= 2 and the node simply retries next round
-//     f,G(Y)  one full pass
+// inside a round and every round costs exactly ONE objective+gradient pass over the histogram:
+//
+//     trial    Z_u  = prox_{lambda/L_u}(Y_u - G_u/L_u)          (soft-threshold on PEN_L1 coordinates)
+//              Y'_u = Z_u + beta_u (Z_u - X_u)                   (momentum; beta = 0 on a gradient restart)
+//     pass     f(Y'), G(Y')                                     (energy + gradient contractions)
+//     accept   descent test at the NEW point against the model built at the old one,
+//                  f(Y') <= f(Y) + <G, Y'-Y> + L/2 |Y'-Y|^2 ,
+//              which must hold for any pair of points once L bounds the curvature.  Passed: X <- Z,
+//              (Y, G, f) <- (Y', G', f').  Failed: L_u *= 2 and the node retries from the same (Y, G).
+//
+// Testing the lemma at Y' instead of at Z saves the separate objective-only pass of textbook
+// backtracking FISTA; it probes the curvature along the direction the iterate actually moves.
 // The problem solved per node is the reference's (src/GraphicalModelLearning.jl:169-177 etc.) with
 // the slack variables z eliminated: min f_u(x) + lambda*sum_{pen} |x_j|.
 #include "common.cuh"
 
+#include <chrono>
 #include <memory>
 
 namespace gml {
@@ -19,8 +26,8 @@ struct FistaState {
     int Nn, Fp, form;
     double lambda, tol, lattice_inv, lattice, eps_f;
     const uint8_t* pen;
-    double *X, *Z, *Y, *G;
-    double *fY, *fZ, *fX, *L, *t, *q, *c, *gmap, *obj;
+    double *X, *Z, *Y, *Yn, *G, *Gn;
+    double *fY, *fYn, *L, *t, *tn, *q, *c, *gmap, *obj;
     double* best;     // smallest gradient-mapping norm seen
     int *stall, *streak;
     int* status;      // 0 active, 1 converged, 2 stalled at the gradient noise floor
@@ -51,13 +58,14 @@ __device__ __forceinline__ double snap(double v, const FistaState& s) {
     return s.lattice_inv > 0.0 ? rint(fmin(fmax(v, -7.9), 7.9) * s.lattice_inv) * s.lattice : v;
 }
 
+// Z = prox step from (Y, G);  Y' = Z + beta (Z - X);  model terms of the descent test at Y'
 __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
     const int u = blockIdx.x;
     if (s.status[u]) return;
     __shared__ double red[4];
     const double L = s.L[u], thr = s.lambda / L;
     const int64_t o = (int64_t)u * s.Fp;
-    double q1 = 0.0, q2 = 0.0, dm = 0.0;
+    double dm = 0.0, r = 0.0;
     for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
         const uint8_t pc = s.pen[o + f];
         const double y = s.Y[o + f], g = s.G[o + f];
@@ -68,65 +76,71 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
             z = snap(z, s);
         }
         s.Z[o + f] = z;
-        const double d = z - y;
-        q1 += g * d; q2 += d * d; dm = fmax(dm, fabs(d));
+        dm = fmax(dm, fabs(z - y));
+        r += (y - z) * (z - s.X[o + f]);          // gradient-scheme adaptive restart: <Y - Z, Z - X> > 0
     }
-    q1 = block_sum(q1, red); q2 = block_sum(q2, red); dm = block_max(dm, red);
+    dm = block_max(dm, red);
+    r = block_sum(r, red);
+    const double t = s.t[u];
+    const bool restart = r > 0.0;
+    const double tn = restart ? 1.0 : 0.5 * (1.0 + sqrt(1.0 + 4.0 * t * t));
+    const double beta = restart ? 0.0 : (t - 1.0) / tn;
+    double q1 = 0.0, q2 = 0.0;
+    for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
+        const double z = s.Z[o + f], y = s.Y[o + f];
+        const double yn = snap(z + beta * (z - s.X[o + f]), s);
+        s.Yn[o + f] = yn;
+        const double d = yn - y;
+        q1 += s.G[o + f] * d; q2 += d * d;
+    }
+    q1 = block_sum(q1, red); q2 = block_sum(q2, red);
     if (threadIdx.x == 0) {
         s.q[u] = q1 + 0.5 * L * q2;
         s.c[u] = 0.5 * L * q2;
-        s.gmap[u] = L * dm;
+        s.gmap[u] = L * dm;          // max-norm of the prox-gradient mapping at Y
+        s.tn[u] = tn;
     }
 }
 
 __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
     const int u = blockIdx.x;
     if (s.status[u]) return;
-    __shared__ double red[4];
     const int64_t o = (int64_t)u * s.Fp;
-    const double fY = s.fY[u], fZ = s.fZ[u];
+    const double gm = s.gmap[u];
+    // ---- convergence is decided at Y (whose gradient is known): the prox point Z is the answer
+    if (gm <= s.tol) {
+        for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) s.X[o + f] = s.Z[o + f];
+        if (threadIdx.x == 0) s.status[u] = 1;
+        return;
+    }
+    const double fY = s.fY[u], fN = s.fYn[u];
     // Upper bound of the evaluation noise of f (fp32 per-sample terms): relative for the RISE/RPLE sums,
-    // absolute for logRISE (f = log Z).  D = f(Y) + q - f(Z) is the slack of the sufficient-decrease
-    // test; for a locally quadratic f, D/c = 1 - L_dir/L with L_dir the curvature along Z - Y.
+    // absolute for logRISE (f = log Z).  D is the slack of the descent test; for a locally quadratic f,
+    // D/c = 1 - L_dir/L with L_dir the curvature along Y' - Y.
     const double noise = s.eps_f * (s.form == GML_B200_LOGRISE ? fmax(fabs(fY), 1.0) : fmax(fabs(fY), 1e-300));
-    const double c = s.c[u], D = fY + s.q[u] - fZ;
+    const double c = s.c[u], D = fY + s.q[u] - fN;
     const bool measurable = c > 10.0 * noise;
     // Reject only a violation that is significant against both the noise and c (L more than ~10% below
     // the directional curvature).  Steps inside the noise floor cannot be verified: they keep the L
     // validated by the larger steps before them; should such an L be too small the steps grow until
     // the test is measurable again.
-    const bool reject = !isfinite(fZ) || (measurable && D < -(0.1 * c + noise));
+    const bool reject = !isfinite(fN) || (measurable && D < -(0.1 * c + noise));
     if (reject) {
         if (threadIdx.x == 0) { s.L[u] *= 2.0; s.streak[u] = 0; atomicAdd(s.n_active, 1); }
         return;
     }
-    // gradient-scheme adaptive restart: <Y - Z, Z - X> > 0
-    double r = 0.0;
-    for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) r += (s.Y[o + f] - s.Z[o + f]) * (s.Z[o + f] - s.X[o + f]);
-    r = block_sum(r, red);
-    const double t = s.t[u];
-    const bool restart = r > 0.0;
-    const double tn = restart ? 1.0 : 0.5 * (1.0 + sqrt(1.0 + 4.0 * t * t));
-    const double beta = restart ? 0.0 : (t - 1.0) / tn;
-    const double gm = s.gmap[u];
-    // stagnation: the gradient mapping stopped improving (noise floor of the gradient)
     int stall = s.stall[u];
     double best = s.best[u];
     if (gm < 0.9 * best) { best = gm; stall = 0; } else ++stall;
-    const bool conv = gm <= s.tol;
-    const bool stalled = !conv && stall >= 200;
-    double l1 = 0.0;
+    const bool stalled = stall >= 200;       // the gradient mapping stopped improving: gradient noise floor
     for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
-        const double z = s.Z[o + f], x = s.X[o + f];
-        s.Y[o + f] = (conv || stalled) ? z : snap(z + beta * (z - x), s);
-        s.X[o + f] = z;
-        if (s.pen[o + f] == PEN_L1) l1 += fabs(z);
+        s.X[o + f] = s.Z[o + f];
+        s.Y[o + f] = s.Yn[o + f];
+        s.G[o + f] = s.Gn[o + f];
     }
-    l1 = block_sum(l1, red);
     if (threadIdx.x == 0) {
-        s.t[u] = tn;
-        s.fX[u] = fZ;
-        s.obj[u] = fZ + s.lambda * l1;
+        s.t[u] = s.tn[u];
+        s.fY[u] = fN;
         s.best[u] = best; s.stall[u] = stall;
         // L is relaxed after three consecutive measurable steps that passed with L > 1.33 L_dir, so it
         // tracks the local curvature (which drops along the path for RPLE) within [0.9, 1.33] L_dir
@@ -134,32 +148,44 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
         if (measurable) streak = (D > 0.25 * c) ? streak + 1 : 0;
         if (streak >= 3) { s.L[u] *= 0.85; streak = 0; }
         s.streak[u] = streak;
-        if (conv) s.status[u] = 1;
-        else if (stalled) s.status[u] = 2;
-        else atomicAdd(s.n_active, 1);
+        if (stalled) s.status[u] = 2; else atomicAdd(s.n_active, 1);
     }
 }
 
 __global__ void fista_init_kernel(FistaState s, double L0) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= s.Nn) return;
-    s.L[u] = L0; s.t[u] = 1.0; s.status[u] = 0; s.gmap[u] = 1e300; s.obj[u] = 0.0; s.fX[u] = 0.0;
+    s.L[u] = L0; s.t[u] = 1.0; s.status[u] = 0; s.gmap[u] = 1e300; s.obj[u] = 0.0;
     s.best[u] = 1e300; s.stall[u] = 0; s.streak[u] = 0;
+}
+
+// obj_u = f_u(X) + lambda |X_pen|_1
+__global__ void __launch_bounds__(128) fista_objective_kernel(FistaState s, const double* __restrict__ fX) {
+    const int u = blockIdx.x;
+    __shared__ double red[4];
+    const int64_t o = (int64_t)u * s.Fp;
+    double l1 = 0.0;
+    for (int f = threadIdx.x; f < s.Fp; f += blockDim.x)
+        if (s.pen[o + f] == PEN_L1) l1 += fabs(s.X[o + f]);
+    l1 = block_sum(l1, red);
+    if (threadIdx.x == 0) s.obj[u] = fX[u] + s.lambda * l1;
 }
 
 }  // namespace
 
 void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, SolveResult& r, cudaStream_t st) {
     const int Nn = prob.Nn, Fp = prob.Fp;
+    auto tick = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = tick();
     std::unique_ptr<EvalBackend> be(backend == GML_B200_SOLVER_FISTA_TC ? make_backend_tc(prob, st)
                                                                         : make_backend_cc(prob, st));
     be->set_profiling(o.reserved[0] != 0);
     const size_t nx = (size_t)Nn * Fp;
-    DevBuf<double> Z, Y, G, fY, fZ, fX, L, t, q, c, gmap, best;
+    DevBuf<double> Z, Y, Yn, G, Gn, fY, fYn, L, t, tn, q, c, gmap, best;
     DevBuf<int> status, n_active, stall, streak;
     r.x.alloc(nx); r.objective.alloc(Nn);
-    Z.alloc(nx); Y.alloc(nx); G.alloc(nx);
-    fY.alloc(Nn); fZ.alloc(Nn); fX.alloc(Nn); L.alloc(Nn); t.alloc(Nn); q.alloc(Nn); c.alloc(Nn); gmap.alloc(Nn);
+    Z.alloc(nx); Y.alloc(nx); Yn.alloc(nx); G.alloc(nx); Gn.alloc(nx);
+    fY.alloc(Nn); fYn.alloc(Nn); L.alloc(Nn); t.alloc(Nn); tn.alloc(Nn); q.alloc(Nn); c.alloc(Nn); gmap.alloc(Nn);
     status.alloc(Nn); n_active.alloc(1); best.alloc(Nn); stall.alloc(Nn); streak.alloc(Nn);
     GML_CUDA(cudaMemsetAsync(r.x.p, 0, nx * sizeof(double), st));
     GML_CUDA(cudaMemsetAsync(Y.p, 0, nx * sizeof(double), st));
@@ -173,10 +199,12 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     s.eps_f = 1e-6;   // generous upper bound of the evaluation noise of f
     s.best = best.p; s.stall = stall.p; s.streak = streak.p;
     s.pen = prob.pen.p;
-    s.X = r.x.p; s.Z = Z.p; s.Y = Y.p; s.G = G.p;
-    s.fY = fY.p; s.fZ = fZ.p; s.fX = fX.p; s.L = L.p; s.t = t.p; s.q = q.p; s.c = c.p; s.gmap = gmap.p;
+    s.X = r.x.p; s.Z = Z.p; s.Y = Y.p; s.Yn = Yn.p; s.G = G.p; s.Gn = Gn.p;
+    s.fY = fY.p; s.fYn = fYn.p; s.L = L.p; s.t = t.p; s.tn = tn.p; s.q = q.p; s.c = c.p; s.gmap = gmap.p;
     s.obj = r.objective.p; s.status = status.p; s.n_active = n_active.p;
 
+    double t_setup = 0, t_loop = 0;
+    if (o.verbose > 0) { GML_CUDA(cudaStreamSynchronize(st)); t_setup = tick(); }
     fista_init_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s, 1.0);
     GML_LAUNCHED();
     be->eval(Y.p, true, fY.p, G.p, st);
@@ -185,7 +213,7 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     for (; it < max_iter; ++it) {
         fista_trial_kernel<<<Nn, 128, 0, st>>>(s);
         GML_LAUNCHED();
-        be->eval(Z.p, false, fZ.p, nullptr, st); ++n_f;
+        be->eval(Yn.p, true, fYn.p, Gn.p, st); ++n_fg;
         GML_CUDA(cudaMemsetAsync(n_active.p, 0, sizeof(int), st));
         fista_accept_kernel<<<Nn, 128, 0, st>>>(s);
         GML_LAUNCHED();
@@ -193,25 +221,32 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
         GML_CUDA(cudaStreamSynchronize(st));
         if (o.verbose > 1) fprintf(stderr, "[gml_b200] fista round %d active %d\n", it, active);
         if (active == 0) { ++it; break; }
-        be->eval(Y.p, true, fY.p, G.p, st); ++n_fg;
     }
+    if (o.verbose > 0) { GML_CUDA(cudaStreamSynchronize(st)); t_loop = tick(); }
+    // objective at the returned point
+    be->eval(r.x.p, false, fYn.p, nullptr, st); ++n_f;
+    fista_objective_kernel<<<Nn, 128, 0, st>>>(s, fYn.p);
+    GML_LAUNCHED();
+
     std::vector<double> hg(Nn);
     std::vector<int> hs(Nn);
     GML_CUDA(cudaMemcpyAsync(hg.data(), gmap.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost, st));
     GML_CUDA(cudaMemcpyAsync(hs.data(), status.p, sizeof(int) * Nn, cudaMemcpyDeviceToHost, st));
     GML_CUDA(cudaStreamSynchronize(st));
     if (o.verbose > 0) {
-        std::vector<double> hL(Nn), hq(Nn), hc(Nn), hfY(Nn), hfZ(Nn), ht(Nn);
+        fprintf(stderr, "[gml_b200] fista: setup %.2f ms, %d rounds %.2f ms, final %.2f ms\n", t_setup - t_begin, it,
+                t_loop - t_setup, tick() - t_loop);
+        std::vector<double> hL(Nn), hq(Nn), hc(Nn), hfY(Nn), hfN(Nn), ht(Nn);
         GML_CUDA(cudaMemcpy(hL.data(), L.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));
         GML_CUDA(cudaMemcpy(hq.data(), q.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));
         GML_CUDA(cudaMemcpy(hc.data(), c.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));
         GML_CUDA(cudaMemcpy(hfY.data(), fY.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));
-        GML_CUDA(cudaMemcpy(hfZ.data(), fZ.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));
+        GML_CUDA(cudaMemcpy(hfN.data(), fYn.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));
         GML_CUDA(cudaMemcpy(ht.data(), t.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));
         for (int u = 0; u < Nn; ++u)
-            if (!hs[u] || o.verbose > 2)
-                fprintf(stderr, "[gml_b200] node %d status %d L %.6g t %.4g gmap %.3e q %.3e c %.3e fY %.17g fZ %.17g D %.3e\n",
-                        u, hs[u], hL[u], ht[u], hg[u], hq[u], hc[u], hfY[u], hfZ[u], hfY[u] + hq[u] - hfZ[u]);
+            if (hs[u] != 1 || o.verbose > 2)
+                fprintf(stderr, "[gml_b200] node %d status %d L %.6g t %.4g gmap %.3e q %.3e c %.3e fY %.17g fX %.17g\n",
+                        u, hs[u], hL[u], ht[u], hg[u], hq[u], hc[u], hfY[u], hfN[u]);
     }
     double mr = 0.0; int unconv = 0;
     // a node stalled at the gradient noise floor counts as converged when it is within 10x tol
