@@ -6,7 +6,10 @@ import ctypes
 import pathlib
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libgml_b200.so"
+import os
+
+# GML_B200_LIB_PATH selects an experimental build variant (developer A/B runs); default = the in-tree product
+LIB_PATH = pathlib.Path(os.environ.get("GML_B200_LIB_PATH", str(_HERE / "libgml_b200.so")))
 
 OK, EINVAL, ECUDA, ENOTCONV = 0, 1, 2, 3
 RISE_ID, LOGRISE_ID, RPLE_ID = 0, 1, 2
@@ -43,6 +46,7 @@ class Stats(ctypes.Structure):
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
         d["energy_fg_ms"], d["grad_ms"], d["energy_f_ms"] = self.reserved_d[0], self.reserved_d[1], self.reserved_d[2]
+        d["timed_full_passes"] = int(self.reserved_d[3])
         return d
 
 

@@ -81,6 +81,7 @@ class B200(GMLMethod):
     device: int = 0
     verbose: int = 0
     profile: bool = False         # time the contraction kernels with CUDA events (stats energy_*_ms / grad_ms)
+    multilevel: bool = False      # FISTA: solve on strided sample subsets first (warm starts); opt-in
     last_stats: dict = field(default_factory=dict, repr=False, compare=False)
 
     def _opts(self, node_begin: int = 0, node_end: int = 0, stream: int = 0) -> _lib.Opts:
@@ -94,6 +95,7 @@ class B200(GMLMethod):
         o.node_begin, o.node_end = int(node_begin), int(node_end)
         o.stream = ctypes.c_void_p(stream) if stream else None
         o.reserved[0] = 1 if self.profile else 0
+        o.reserved[1] = 1 if self.multilevel else 0
         return o
 
 

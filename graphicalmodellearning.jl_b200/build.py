@@ -29,8 +29,13 @@ def _stale(target: pathlib.Path, deps) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), suffix: str = "") -> pathlib.Path:
+    """suffix / extra_flags build an experimental variant (libgml_b200<suffix>.so) next to the product."""
+    global OBJ, LIB
     nvcc = _nvcc()
+    if suffix:
+        OBJ = HERE / ("build" + suffix)
+        LIB = HERE / f"libgml_b200{suffix}.so"
     OBJ.mkdir(exist_ok=True)
     sources = sorted(CSRC.glob("*.cu"))
     headers = sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "gml_b200.h"]
@@ -42,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -64,4 +69,6 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    suffix = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--suffix=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=extra, suffix=suffix))

@@ -148,7 +148,8 @@ void finish_stats(gml_b200_stats* stats, const SolveResult& r, int solver_used, 
     stats->n_f_passes = r.n_f;
     stats->n_unconverged = r.n_unconverged;
     stats->kernel_launches = g_launches;
-    stats->evals = (double)Nn * (double)K * (r.n_fg + 0.5 * r.n_f);
+    const double fg = r.fg_units >= 0.0 ? r.fg_units : r.n_fg, fo = r.f_units >= 0.0 ? r.f_units : r.n_f;
+    stats->evals = (double)Nn * (double)K * (fg + 0.5 * fo);
     stats->solve_ms = solve_ms;
     stats->d2h_ms = d2h_ms;
     stats->total_ms += now_ms() - t0;

@@ -105,6 +105,7 @@ struct NodeProblem {
 
 struct SolveResult {
     double profile[4] = {0, 0, 0, 0};
+    double fg_units = -1.0, f_units = -1.0;   // passes weighted by the fraction of the histogram they swept (< 0: use n_fg / n_f)
     DevBuf<double> x;         // [Nn x Fp]
     DevBuf<double> objective; // [Nn]  f_u(x) + lambda*|x_pen|_1
     int iterations = 0, n_fg = 0, n_f = 0, n_unconverged = 0;
@@ -122,6 +123,8 @@ void build_multibody_features(Histogram& h, int order, const std::vector<int32_t
 const int8_t* ensure_P(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st);
 // sample-blocked copy [Kp/128][Fp][128] of Q [Fp x Kp] (cached in h.Qb): every 128-sample tile is contiguous
 const int8_t* ensure_Qb(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st);
+// sum of w over the samples of every `stride`-th 128-sample block
+double subsample_weight(const Histogram& h, int64_t stride, cudaStream_t st);
 void launch_block_copy(const int8_t* Q, int8_t* Qb, int Fp, int64_t Kp, cudaStream_t st);
 
 // --- newton.cu : fp64 proximal-Newton / barrier-Newton for small feature counts
@@ -139,7 +142,11 @@ struct EvalBackend {
     virtual void eval(const double* x, bool want_grad, double* f_out, double* g_out, cudaStream_t st) = 0;
     virtual double lattice() const { return 0.0; }
     // optional per-kernel device timing (opts.reserved[0] != 0): out[0] = energy-kernel ms (full passes),
-    // out[1] = gradient-kernel ms, out[2] = energy-kernel ms (objective-only passes), out[3] unused
+    // out[1] = gradient-kernel ms, out[2] = energy-kernel ms (objective-only passes), out[3] = number of timed full passes
+    // (only launches that sweep the whole histogram are timed)
+    // Restrict the passes to every `stride`-th block of 128 samples; returns the weight mass rho of the
+    // subset (sum of w over the used samples), or a negative value when the backend cannot subsample.
+    virtual double set_subsample(int64_t /*stride*/, cudaStream_t) { return -1.0; }
     virtual void set_profiling(bool) {}
     virtual void collect_profile(double* /*out4*/) {}
 };

@@ -171,7 +171,8 @@ struct EnergyParams {
     int64_t Kp;
     int Fp, Fspin, Nn, n_tiles, node_begin_row;   // node tile t covers spin rows node_begin_row + 64 t ... of each [Fspin x 128] block
     int n_groups;                          // sample ranges; work item = (group, node tile)
-    int64_t sample_blocks;                 // Kp / 128
+    int64_t sample_blocks;                 // sample blocks of this pass (Kp / 128 / block_stride)
+    int64_t block_stride;                  // pass b uses histogram block b * block_stride (strided subsample)
     int64_t r_rows_per_limb;               // Nn_pad2
     int nR, form, debug_skip_math;
     const float* w32;
@@ -180,7 +181,10 @@ struct EnergyParams {
 };
 
 constexpr int E_STAGES = 3;
-constexpr int E_EPI_WARPS = 8;                       // two per TMEM lane quarter, 32 nodes each
+#ifndef GML_E_EPI_WARPS
+#define GML_E_EPI_WARPS 16   // measured: full pass 4.17 ms (8 warps) -> 3.50 ms (16 warps) at N=1000, K=1e6
+#endif
+constexpr int E_EPI_WARPS = GML_E_EPI_WARPS;         // E_EPI_WARPS/4 per TMEM lane quarter, 64/(E_EPI_WARPS/4) nodes each
 constexpr int E_THREADS = 64 + 32 * E_EPI_WARPS;
 constexpr int E_A_BYTES = 128 * 128, E_B_BYTES = 256 * 128, E_STAGE_BYTES = E_A_BYTES + E_B_BYTES;
 constexpr int E_S_BYTES = NODE_TILE1 * 128;          // spins tile of the node block
@@ -258,7 +262,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int nt; int64_t b0, b1;
                 item_range(item, nt, b0, b1);
-                for (int64_t sb = b0; sb < b1; ++sb) {
+                for (int64_t eb = b0; eb < b1; ++eb) {
+                    const int64_t sb = eb * p.block_stride;
                     mbar_wait(&sempty[slot], sphase ^ 1);
                     mbar_expect_tx(&sfull[slot], E_S_BYTES);
                     tma_load_2d(s_spin + slot * E_S_BYTES, &tmS, &sfull[slot], 0, (int)(sb * p.Fspin) + p.node_begin_row + nt * NODE_TILE1);
@@ -305,10 +310,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
     } else {
         // ================= epilogue warps 2..9: TMEM lane quarter = warp % 4, node half = (warp-2)/4 =========
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 2) >> 2;                // which slice of the node tile this warp owns
         const int row = quarter * 32 + lane;            // sample within the block == TMEM lane
         const int et = threadIdx.x - 64;                // 0..255
-        constexpr int NPT = NODE_TILE1 / 2;             // nodes per thread
+        constexpr int NPT = NODE_TILE1 / (E_EPI_WARPS / 4);   // nodes per thread
         constexpr int EPI_THREADS = 32 * E_EPI_WARPS;
         float facc[NPT];
         int as = 0; uint32_t aphase = 0;
@@ -333,7 +338,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                     facc[i] = 0.f;
                 }
             };
-            for (int64_t sb = b0; sb < b1; ++sb) {
+            for (int64_t eb = b0; eb < b1; ++eb) {
+                const int64_t sb = eb * p.block_stride;
                 // objective terms: fp32 per-thread partial sums over at most 32 sample blocks, then fp64
                 if (since_flush >= 32) { flush(); since_flush = 0; }
                 ++since_flush;
@@ -434,7 +440,7 @@ struct GradParams {
     int Fp, m_tiles, f_tiles, nR;
     int64_t r_rows_per_limb;      // Nn_pad2
     int n_splits;                 // sample ranges; work item = (split, output tile)
-    int64_t sample_blocks;
+    int64_t sample_blocks, block_stride;   // as in EnergyParams
     long long* G;                 // [Nn_pad2 x Fp] int64
 };
 
@@ -489,7 +495,8 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int mt, ft; int64_t b0, b1;
                 decode(item, mt, ft, b0, b1);
-                for (int64_t b = b0; b < b1; ++b) {
+                for (int64_t eb = b0; eb < b1; ++eb) {
+                    const int64_t b = eb * p.block_stride;
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     uint8_t* s = smem + stage * STAGE_BYTES;
@@ -691,25 +698,33 @@ struct BackendTC : EvalBackend {
 
     double lattice() const override { return X_LATTICE; }
 
+    // ---- strided sample subsets (multilevel continuation): a pass uses every `stride`-th 128-sample block
+    int64_t stride = 1;
+    double set_subsample(int64_t new_stride, cudaStream_t st) override {
+        stride = std::max<int64_t>(1, new_stride);
+        return subsample_weight(*p.hist, stride, st);
+    }
+
     // ---- per-kernel timing with CUDA events on the launch stream
     bool profiling = false;
     struct Span { cudaEvent_t a, b; int kind; };
     std::vector<Span> spans;
     void set_profiling(bool on) override { profiling = on; }
     void span_begin(int kind, cudaStream_t st) {
-        if (!profiling) return;
+        if (!profiling || stride != 1) return;   // only full-histogram launches are timed
         Span s; s.kind = kind;
         GML_CUDA(cudaEventCreate(&s.a)); GML_CUDA(cudaEventCreate(&s.b));
         GML_CUDA(cudaEventRecord(s.a, st));
         spans.push_back(s);
     }
-    void span_end(cudaStream_t st) { if (profiling) GML_CUDA(cudaEventRecord(spans.back().b, st)); }
+    void span_end(cudaStream_t st) { if (profiling && stride == 1) GML_CUDA(cudaEventRecord(spans.back().b, st)); }
     void collect_profile(double* out) override {
         for (auto& s : spans) {
             float ms = 0.f;
             GML_CUDA(cudaEventSynchronize(s.b));
             GML_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
             out[s.kind] += ms;
+            if (s.kind == 0) out[3] += 1.0;      // number of timed full passes
             cudaEventDestroy(s.a); cudaEventDestroy(s.b);
         }
         spans.clear();
@@ -723,7 +738,7 @@ struct BackendTC : EvalBackend {
         GML_CUDA(cudaMemsetAsync(fsum.p, 0, sizeof(double) * Nn_pad1, st));
         EnergyParams ep{};
         ep.Kp = h.Kp; ep.Fp = p.Fp; ep.Fspin = Fspin; ep.Nn = p.Nn; ep.n_tiles = Nn_pad1 / NODE_TILE1;
-        ep.sample_blocks = h.Kp / 128; ep.r_rows_per_limb = Nn_pad2; ep.nR = nR; ep.form = p.form;
+        ep.block_stride = stride; ep.sample_blocks = ceil_div(h.Kp / 128, stride); ep.r_rows_per_limb = Nn_pad2; ep.nR = nR; ep.form = p.form;
         ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p;
         ep.debug_skip_math = std::getenv("GML_TC_DEBUG_SKIP_MATH") ? 1 : 0;
         ep.node_begin_row = first_row;
@@ -744,7 +759,7 @@ struct BackendTC : EvalBackend {
             GML_CUDA(cudaMemsetAsync(G64.p, 0, sizeof(long long) * Nn_pad2 * p.Fp, st));
             GradParams gp{};
             gp.Fp = p.Fp; gp.m_tiles = Nn_pad2 / 128; gp.f_tiles = p.Fp / 128; gp.nR = nR;
-            gp.r_rows_per_limb = Nn_pad2; gp.sample_blocks = h.Kp / 128; gp.G = G64.p;
+            gp.r_rows_per_limb = Nn_pad2; gp.block_stride = stride; gp.sample_blocks = ceil_div(h.Kp / 128, stride); gp.G = G64.p;
             const int tiles = gp.m_tiles * gp.f_tiles;
             gp.n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / tiles, gp.sample_blocks));
             const int grid2 = std::min(n_sms, tiles * gp.n_splits);

@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
 __global__ void fista_init_kernel(FistaState s, double L0) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= s.Nn) return;
-    s.L[u] = L0; s.t[u] = 1.0; s.status[u] = 0; s.gmap[u] = 1e300; s.obj[u] = 0.0;
+    s.L[u] = L0 > 0.0 ? L0 : s.L[u] * -L0;      // first level: initial estimate; later levels: rescale by rho ratio
+    s.t[u] = 1.0; s.status[u] = 0; s.gmap[u] = 1e300; s.obj[u] = 0.0;
     s.best[u] = 1e300; s.stall[u] = 0; s.streak[u] = 0;
 }
 
@@ -193,7 +194,7 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
 
     FistaState s{};
     s.Nn = Nn; s.Fp = Fp; s.form = prob.form; s.lambda = prob.lambda;
-    s.tol = o.tol > 0 ? o.tol : 1e-6;
+    s.tol = o.tol > 0 ? o.tol : 1e-6;   // overwritten per level
     s.lattice = be->lattice();
     s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
     s.eps_f = 1e-6;   // generous upper bound of the evaluation noise of f
@@ -205,26 +206,66 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
 
     double t_setup = 0, t_loop = 0;
     if (o.verbose > 0) { GML_CUDA(cudaStreamSynchronize(st)); t_setup = tick(); }
-    fista_init_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s, 1.0);
-    GML_LAUNCHED();
-    be->eval(Y.p, true, fY.p, G.p, st);
-    int n_fg = 1, n_f = 0, it = 0, active = Nn;
+    // ---- multilevel continuation: solve on strided subsets of the histogram first (every 256th, then every
+    // 16th block of 128 samples), warm-starting each level from the previous one.  A coarse level only needs
+    // the accuracy of its own sampling error (~1/sqrt(M_level)), costs 1/stride of a pass per round, and leaves
+    // the full-data level a start that is ~1e-3 from its optimum instead of |x| ~ 0.4.
+    const Histogram& hist = *prob.hist;
+    const int64_t SB = hist.Kp / 128;
+    std::vector<int64_t> strides;
+    // Opt-in (opts.reserved[1]): on the well-conditioned benchmark problems a cold start converges in ~35-45
+    // rounds and the warm start from a 16x subsample saves fewer rounds than its momentum restart costs
+    // (measured at N=1000, K=1e6: 29 coarse + 40 fine rounds vs 35 cold).
+    const bool can_subsample = o.reserved[1] != 0 && be->set_subsample(1, st) > 0.0;
+    if (can_subsample && SB >= 256 * 64) strides.push_back(256);
+    if (can_subsample && SB >= 16 * 64) strides.push_back(16);
+    strides.push_back(1);
+    const double user_tol = o.tol > 0 ? o.tol : 1e-6;
+    const bool scale_free = prob.form == GML_B200_LOGRISE;     // grad log Z does not scale with the weight mass
+    int n_fg = 0, n_f = 0, it = 0, active = Nn;
+    double fg_units = 0.0, rho_prev = 1.0;
     const int max_iter = o.max_iter > 0 ? o.max_iter : 5000;
-    for (; it < max_iter; ++it) {
-        fista_trial_kernel<<<Nn, 128, 0, st>>>(s);
+    for (size_t li = 0; li < strides.size(); ++li) {
+        const int64_t stride = strides[li];
+        const bool last = li + 1 == strides.size();
+        const double rho = stride > 1 ? be->set_subsample(stride, st) : (can_subsample ? be->set_subsample(1, st) : 1.0);
+        const double scale = scale_free ? 1.0 : rho;
+        // weights are not renormalised: f_level = rho * (normalised f), so lambda, L and the tolerance scale by rho
+        s.lambda = prob.lambda * scale;
+        s.tol = scale * (last ? user_tol : std::max(user_tol, 0.1 / std::sqrt(std::max(hist.M * rho, 1.0))));
+        fista_init_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s, li == 0 ? scale : -(scale_free ? 1.0 : rho / rho_prev));
         GML_LAUNCHED();
-        be->eval(Yn.p, true, fYn.p, Gn.p, st); ++n_fg;
-        GML_CUDA(cudaMemsetAsync(n_active.p, 0, sizeof(int), st));
-        fista_accept_kernel<<<Nn, 128, 0, st>>>(s);
-        GML_LAUNCHED();
-        GML_CUDA(cudaMemcpyAsync(&active, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        GML_CUDA(cudaStreamSynchronize(st));
-        if (o.verbose > 1) fprintf(stderr, "[gml_b200] fista round %d active %d\n", it, active);
-        if (active == 0) { ++it; break; }
+        rho_prev = rho;
+        GML_CUDA(cudaMemcpyAsync(Y.p, r.x.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));   // warm start
+        be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += 1.0 / stride;
+        active = Nn;
+        for (; it < max_iter; ++it) {
+            fista_trial_kernel<<<Nn, 128, 0, st>>>(s);
+            GML_LAUNCHED();
+            be->eval(Yn.p, true, fYn.p, Gn.p, st); ++n_fg; fg_units += 1.0 / stride;
+            GML_CUDA(cudaMemsetAsync(n_active.p, 0, sizeof(int), st));
+            fista_accept_kernel<<<Nn, 128, 0, st>>>(s);
+            GML_LAUNCHED();
+            GML_CUDA(cudaMemcpyAsync(&active, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            GML_CUDA(cudaStreamSynchronize(st));
+            if (o.verbose > 1) {
+                std::vector<double> hg(Nn), hL(Nn);
+                GML_CUDA(cudaMemcpy(hg.data(), gmap.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));
+                GML_CUDA(cudaMemcpy(hL.data(), L.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));
+                double gmax = 0, gsum = 0, lmax = 0, lmin = 1e300;
+                for (int u = 0; u < Nn; ++u) { gmax = std::max(gmax, hg[u]); gsum += hg[u]; lmax = std::max(lmax, hL[u]); lmin = std::min(lmin, hL[u]); }
+                fprintf(stderr, "[gml_b200] fista level %zu (stride %lld) round %d active %d gmap max %.3e mean %.3e L [%.3g, %.3g]\n",
+                        li, (long long)stride, it, active, gmax / scale, gsum / Nn / scale, lmin / scale, lmax / scale);
+            }
+            if (active == 0) { ++it; break; }
+        }
+        if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista level %zu: stride %lld rho %.6g tol %.3g, rounds so far %d\n", li, (long long)stride, rho, s.tol, it);
     }
+    s.lambda = prob.lambda;
     if (o.verbose > 0) { GML_CUDA(cudaStreamSynchronize(st)); t_loop = tick(); }
     // objective at the returned point
     be->eval(r.x.p, false, fYn.p, nullptr, st); ++n_f;
+    r.fg_units = fg_units; r.f_units = 1.0;
     fista_objective_kernel<<<Nn, 128, 0, st>>>(s, fYn.p);
     GML_LAUNCHED();
 

@@ -107,6 +107,13 @@ __global__ void block_i8_kernel(const int8_t* __restrict__ Q, int8_t* __restrict
     *reinterpret_cast<int4*>(Qb + ((sb * Fp + f) * 128) + within * 16) = v;
 }
 
+__global__ void subsample_weight_kernel(const double* __restrict__ w, int64_t blocks, int64_t stride, double* __restrict__ out) {
+    double s = 0.0;
+    for (int64_t b = blockIdx.x; b * stride < blocks; b += gridDim.x) s += w[b * stride * 128 + threadIdx.x];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
 // multibody base features: row f = product of the spins listed in subsets[f*(order-1) ...]
 __global__ void multibody_features_kernel(const int8_t* __restrict__ base, int64_t Kp, const int32_t* __restrict__ subsets,
                                           int width, int F, int8_t* __restrict__ out) {
@@ -199,6 +206,19 @@ const int8_t* ensure_P(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st) {
     GML_LAUNCHED();
     h.P_of = Q;
     return h.P.p;
+}
+
+double subsample_weight(const Histogram& h, int64_t stride, cudaStream_t st) {
+    if (stride <= 1) return 1.0;
+    DevBuf<double> acc;
+    acc.alloc(1);
+    GML_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double), st));
+    subsample_weight_kernel<<<592, 128, 0, st>>>(h.w64.p, h.Kp / 128, stride, acc.p);
+    GML_LAUNCHED();
+    double rho = 0.0;
+    GML_CUDA(cudaMemcpyAsync(&rho, acc.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    GML_CUDA(cudaStreamSynchronize(st));
+    return rho;
 }
 
 void launch_block_copy(const int8_t* Q, int8_t* Qb, int Fp, int64_t Kp, cudaStream_t st) {

@@ -55,7 +55,8 @@ typedef struct gml_b200_opts {
     int32_t node_end;
     int32_t verbose;
     void* stream;       /* cudaStream_t to launch on; NULL = the handle's own stream */
-    int32_t reserved[8]; /* reserved[0] != 0: time the contraction kernels with CUDA events (stats.reserved_d) */
+    int32_t reserved[8]; /* reserved[0] != 0: time the contraction kernels with CUDA events (stats.reserved_d);
+                            reserved[1] != 0: enable the multilevel (sample-subset) continuation of the FISTA solvers */
 } gml_b200_opts;
 
 typedef struct gml_b200_stats {
@@ -66,7 +67,8 @@ typedef struct gml_b200_stats {
     int32_t n_unconverged;    /* nodes that missed tol */
     int32_t reserved_i;
     int64_t kernel_launches;  /* kernels of this library launched by the call */
-    double evals;             /* node*sample evals = nodes*K*(n_fg + 0.5*n_f)   */
+    double evals;             /* node*sample evals = nodes*K*(fg + 0.5*f), passes weighted by the fraction of
+                                 the histogram they swept (coarse continuation levels count 1/stride)   */
     double pack_ms;           /* device: validate + layout build */
     double h2d_ms;            /* host->device copies */
     double solve_ms;          /* device-timed solver (CUDA events on the launch stream) */
@@ -74,7 +76,8 @@ typedef struct gml_b200_stats {
     double total_ms;          /* host wall clock of the whole call */
     double max_residual;      /* largest final stopping residual over nodes */
     double reserved_d[4];     /* profiling: [0] energy kernel ms in full passes, [1] gradient kernel ms,
-                                 [2] energy kernel ms in objective-only passes */
+                                 [2] energy kernel ms in objective-only passes, [3] number of timed full passes
+                                 (only launches over the whole histogram are timed) */
 } gml_b200_stats;
 
 typedef struct gml_b200_handle gml_b200_handle;

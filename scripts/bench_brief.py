@@ -8,7 +8,7 @@ for line in sys.stdin:
     sh = r.get("kernel_ms_share", {})
     it = d["passes"]["iterations"]
     ms = d["ms_per_step"]
-    per = {k: round(v * ms / max(1, (d["passes"]["fg"] if "objective" not in k else d["passes"]["f"])), 3) for k, v in sh.items()}
+    per = {"dominant": r.get("kernel"), "avg_ms": round(r.get("avg_launch_ms", 0), 3), "launches": r.get("launches"), "frac": round(r.get("frac", 0), 3)}
     print(f"learn {ms:.1f} ms  iters {it}  value {d['value']:.3e}  per-launch ms {per}  recon_err {d['max_abs_coupling_error_vs_truth']:.4f} "
           f"resid {d['max_residual']:.1e} clocks {d.get('clocks')}")
     if d.get("e2e"): print("  e2e", d["e2e"])
