@@ -112,6 +112,35 @@ def test_multirise_order3_larger_fista():
         assert max(abs(got[k] - base[k]) for k in base.terms) <= 5e-5
 
 
+def test_multirise_c4_reduced_tensor_path():
+    """BASELINE config C4 reduced to N=12 (exactly samplable): order 3 -> 79 base features, beyond the Newton
+    solver's 64, so the auto solver takes the tensor-core FISTA path; checked against the oracle key by key."""
+    n = 12
+    terms = three_body_model(n, 30)
+    hist = o.sample_exact(terms, n, 200_000, np.random.default_rng(32))
+    ref = c.learn_multibody(hist, 0.4, True, 3)
+    m = B200()
+    got, info = gml_b200.learn(hist, multiRISE(0.4, True, 3), m, return_info=True)
+    assert info["solver_used"] == 3
+    assert got.terms.keys() == ref.keys()
+    assert max(abs(got[k] - ref[k]) for k in ref) <= 1e-5
+    # the strongest learned three-body terms are the true ones
+    triples = {k: v for k, v in got.terms.items() if len(k) == 3}
+    top = sorted(triples, key=lambda k: -abs(triples[k]))[:6]
+    assert all(k in terms for k in top)
+
+
+def test_multilevel_continuation_agrees():
+    """Opt-in strided-subsample warm starts must land on the same optimum."""
+    _, hist = histogram_c1(n=16, m_samples=400_000, seed=16)
+    big = np.repeat(hist.astype(np.float64), 64, axis=0)   # 64 copies of every configuration: K ~ 1e6 rows ...
+    big[:, 0] /= 64.0                                      # ... with the counts split, so M, lambda and the optimum are unchanged
+    big = big[np.random.default_rng(0).permutation(big.shape[0])]
+    a = gml_b200.learn(big, RISE(), B200(solver="fista_tc", multilevel=True))
+    b = gml_b200.learn(hist, RISE(), B200(solver="newton"))
+    assert np.abs(a - b).max() <= 1e-5
+
+
 @pytest.mark.parametrize("n_samples,thr", [(1000, 0.15), (10000, 0.05)])
 @pytest.mark.parametrize("form", list(FORMS))
 def test_learned_model_accuracy(form, n_samples, thr):
