@@ -1,0 +1,103 @@
+"""Full-size checks (BASELINE config C2: N=100 10x10 lattice spin glass, 1e6 samples) through size-independent
+properties: KKT conditions of the returned point verified with an INDEPENDENT gradient (the CUDA-core backend),
+node-shard consistency, recovery of the generating couplings, symmetry."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import gml_b200
+from gml_b200 import B200, RISE, RPLE, _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def lattice_model(side=10, coupling=0.4, seed=100):
+    rng = np.random.default_rng(seed)
+    n = side * side
+    truth = np.zeros((n, n))
+    for r in range(side):
+        for c in range(side):
+            i = r * side + c
+            for j in ([i + 1] if c + 1 < side else []) + ([i + side] if r + 1 < side else []):
+                truth[i, j] = truth[j, i] = coupling * rng.choice([-1.0, 1.0])
+    row_ptr = np.zeros(n + 1, dtype=np.int32)
+    col, val = [], []
+    for i in range(n):
+        nz = np.nonzero(truth[i])[0]
+        row_ptr[i + 1] = row_ptr[i] + len(nz)
+        col += nz.tolist(); val += truth[i, nz].tolist()
+    return truth, row_ptr, np.array(col, dtype=np.int32), np.array(val, dtype=np.float32)
+
+
+@pytest.fixture(scope="module")
+def c2_session():
+    import torch
+    truth, row_ptr, col, val = lattice_model()
+    n, k = 100, 1_000_000
+    spins = torch.empty((n, k), dtype=torch.int8, device="cuda")
+    counts = torch.ones(k, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().gml_b200_sample_gibbs_device(0, n, row_ptr.ctypes.data, col.ctypes.data, val.ctypes.data, None,
+                                                        k, 60, 100, ctypes.c_void_p(spins.data_ptr()), k, None))
+    torch.cuda.synchronize()
+    sess = gml_b200.Session(0).attach_device(counts.data_ptr(), spins.data_ptr(), k, n, k)
+    return sess, truth, spins
+
+
+def rows_to_x(theta):
+    """N x N rows (diagonal = field) -> N x (N+1) coefficient rows (self coupling 0, field last)."""
+    n = theta.shape[0]
+    x = np.zeros((n, n + 1))
+    x[:, :n] = theta
+    x[:, n] = np.diag(theta)
+    x[np.arange(n), np.arange(n)] = 0.0
+    return x
+
+
+@pytest.mark.parametrize("form_cls,c", [(RISE, 0.4), (RPLE, 0.2)])
+def test_c2_kkt_recovery_symmetry(c2_session, form_cls, c):
+    sess, truth, _ = c2_session
+    n = 100
+    theta, info = sess.solve_pairwise(form_cls(c, False), B200(), return_info=True)
+    assert info["solver_used"] == 3 and info["n_unconverged"] == 0
+    lam = info["lambda"]
+    # recovery of the generating model (statistical tolerance at 1e6 samples) and of its support
+    off = theta - np.diag(np.diag(theta))
+    assert np.abs(off - truth).max() <= 0.02
+    assert np.abs(np.diag(theta)).max() <= 0.02
+    # KKT with the independent fp32 CUDA-core gradient: |g_j| <= lambda on zeros, g_j = -lambda sign(x_j) on the
+    # support, g = 0 for the free field.  Tolerance: FISTA tol (1e-6) x curvature + fp32 gradient noise
+    f, g = sess.eval_pairwise(form_cls(c, False), rows_to_x(theta), backend="fista_cc")
+    x = rows_to_x(theta)
+    tol = 2e-5
+    for u in range(n):
+        for j in range(n):
+            if j == u:
+                continue
+            if x[u, j] == 0.0:
+                assert abs(g[u, j]) <= lam + tol
+            else:
+                assert abs(g[u, j] + lam * np.sign(x[u, j])) <= tol
+        assert abs(g[u, n]) <= tol
+    # objective reported by the solver = f + lambda |x|_1 with the independent f
+    obj = f + lam * (np.abs(x[:, :n]).sum(axis=1))
+    assert np.allclose(info["objective"], obj, rtol=2e-6, atol=0)
+    # symmetrised output is symmetric and equals 0.5 (R + R')
+    sym = sess.solve_pairwise(form_cls(c, True), B200())
+    assert np.array_equal(sym, sym.T)
+    assert np.abs(sym - 0.5 * (theta + theta.T)).max() <= 1e-12
+
+
+def test_c2_node_shards_equal_full_solve(c2_session):
+    """Node problems are independent: solving shards [0,37) and [37,100) gives the rows of the full solve."""
+    import torch
+    sess, _, _ = c2_session
+    n = 100
+    full = sess.solve_pairwise(RISE(0.4, False), B200())
+    rows = []
+    for b, e in ((0, 37), (37, 100)):
+        out = torch.empty((e - b, n), dtype=torch.float64, device="cuda")
+        sess.solve_pairwise_device(RISE(0.4, False), B200(), out.data_ptr(), b, e)
+        torch.cuda.synchronize()
+        rows.append(out.cpu().numpy())
+    assert np.abs(np.vstack(rows) - full).max() <= 1e-9
