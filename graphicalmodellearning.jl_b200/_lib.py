@@ -23,7 +23,7 @@ EXPORTS = (
     "gml_b200_attach_histogram_device", "gml_b200_num_samples", "gml_b200_solve_pairwise",
     "gml_b200_solve_pairwise_device", "gml_b200_solve_multibody", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
     "gml_b200_symmetrize_device",
-    "gml_b200_sample_gibbs_device",
+    "gml_b200_sample_gibbs_device", "gml_b200_build_histogram_device",
 )
 
 
@@ -99,6 +99,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gml_b200_symmetrize_device.argtypes = [vp, c.c_int32, vp]
     lib.gml_b200_sample_gibbs_device.argtypes = [c.c_int32, c.c_int32, vp, vp, vp, vp, c.c_int64, c.c_int32,
                                                  c.c_uint64, vp, c.c_int64, vp]
+    lib.gml_b200_build_histogram_device.argtypes = [c.c_int32, vp, c.c_int64, c.c_int32, c.c_int64, vp, c.c_int64, vp,
+                                                    c.POINTER(c.c_int64), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is c.c_int and name not in ("gml_b200_device_count",):

@@ -605,4 +605,15 @@ int gml_b200_sample_gibbs_device(int32_t device, int32_t N, const int32_t* row_p
     });
 }
 
+int gml_b200_build_histogram_device(int32_t device, const int8_t* d_samples, int64_t M, int32_t N, int64_t ld,
+                                    int8_t* d_out_spins, int64_t ld_out, double* d_out_counts, int64_t* out_K,
+                                    void* stream) {
+    return guarded([&] {
+        GML_REQUIRE(d_samples && d_out_spins && d_out_counts && out_K, "null argument");
+        GML_REQUIRE(ld >= M, "ld must be >= M");
+        GML_CUDA(cudaSetDevice(device));
+        *out_K = build_histogram(d_samples, M, N, ld, d_out_spins, ld_out, d_out_counts, (cudaStream_t)stream);
+    });
+}
+
 }  // extern "C"

@@ -156,6 +156,10 @@ EvalBackend* make_backend_tc(const NodeProblem& p, cudaStream_t st);
 // --- output.cu
 void symmetrize_rowmajor(double* d_theta, int N, cudaStream_t st);
 
+// --- histogram.cu : raw samples -> deduplicated histogram (returns the number of distinct configurations)
+int64_t build_histogram(const int8_t* d_samples, int64_t M, int N, int64_t ld, int8_t* d_out_spins, int64_t ld_out,
+                        double* d_out_counts, cudaStream_t st);
+
 // --- sampler.cu
 void sample_gibbs(int N, const int32_t* d_row_ptr, const int32_t* d_col, const float* d_J, const float* d_h,
                   int max_deg, int64_t n_samples, int sweeps, uint64_t seed, int8_t* d_spins, int64_t ld,

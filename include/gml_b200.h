@@ -161,6 +161,14 @@ int gml_b200_sample_gibbs_device(int32_t device, int32_t N, const int32_t* row_p
                                  const float* coupling, const float* field, int64_t n_samples,
                                  int32_t sweeps, uint64_t seed, int8_t* d_spins, int64_t ld, void* stream);
 
+/* ---- histogram builder: replaces the host `countmap` of src/sampling.jl:52-54 -----------------
+ * d_samples: M raw samples, int8 spin-major [N x ld] in device memory, N <= 64.  Writes the K distinct
+ * configurations to d_out_spins (int8 spin-major, leading dimension ld_out >= K) and their multiplicities to
+ * d_out_counts; *out_K receives K.  Rows come out sorted by the bit-packed configuration (bit i = spin i+1 up). */
+int gml_b200_build_histogram_device(int32_t device, const int8_t* d_samples, int64_t M, int32_t N, int64_t ld,
+                                    int8_t* d_out_spins, int64_t ld_out, double* d_out_counts, int64_t* out_K,
+                                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,3 +101,39 @@ def test_c2_node_shards_equal_full_solve(c2_session):
         torch.cuda.synchronize()
         rows.append(out.cpu().numpy())
     assert np.abs(np.vstack(rows) - full).max() <= 1e-9
+
+
+def test_device_histogram_builder_and_sampler():
+    """raw Gibbs samples (N=16, M=1e6) -> device dedup -> learn; the device histogram equals the
+    host np.unique histogram, and learn() on it recovers the generating model (test/runtests.jl:105-127 style)."""
+    import torch
+    from helpers import random_ising
+    n, m = 16, 1_000_000
+    model = random_ising(n, 16)
+    row_ptr = np.zeros(n + 1, dtype=np.int32); col, val = [], []
+    for i in range(n):
+        nz = [j for j in range(n) if j != i and model[i, j] != 0.0]
+        row_ptr[i + 1] = row_ptr[i] + len(nz); col += nz; val += [model[i, j] for j in nz]
+    col, val = np.array(col, dtype=np.int32), np.array(val, dtype=np.float32)
+    field = np.ascontiguousarray(np.diag(model), dtype=np.float32)
+    lib = _lib.load()
+    raw = torch.empty((n, m), dtype=torch.int8, device="cuda")
+    _lib.check(lib.gml_b200_sample_gibbs_device(0, n, row_ptr.ctypes.data, col.ctypes.data, val.ctypes.data, field.ctypes.data,
+                                                m, 60, 5, ctypes.c_void_p(raw.data_ptr()), m, None))
+    out_spins = torch.empty((n, m), dtype=torch.int8, device="cuda")
+    out_counts = torch.empty(m, dtype=torch.float64, device="cuda")
+    k = ctypes.c_int64(0)
+    _lib.check(lib.gml_b200_build_histogram_device(0, ctypes.c_void_p(raw.data_ptr()), m, n, m, ctypes.c_void_p(out_spins.data_ptr()),
+                                                   m, ctypes.c_void_p(out_counts.data_ptr()), ctypes.byref(k), None))
+    K = k.value
+    assert 1000 < K <= 65536
+    host = raw.cpu().numpy()
+    keys = (host.T > 0).astype(np.uint64) @ (np.uint64(1) << np.arange(n, dtype=np.uint64))
+    uk, uc = np.unique(keys, return_counts=True)
+    assert K == len(uk)
+    dev_spins = out_spins[:, :K].cpu().numpy()
+    dev_keys = (dev_spins.T > 0).astype(np.uint64) @ (np.uint64(1) << np.arange(n, dtype=np.uint64))
+    assert np.array_equal(dev_keys, uk) and np.array_equal(out_counts[:K].cpu().numpy(), uc.astype(np.float64))
+    hist = np.concatenate([out_counts[:K].cpu().numpy()[:, None], dev_spins.T.astype(np.float64)], axis=1)
+    learned = gml_b200.learn(hist, RISE())
+    assert np.abs(learned - model).max() <= 0.02
