@@ -115,6 +115,7 @@ def cpu_baseline(spins_sample: np.ndarray, counts_sample: np.ndarray, nodes, lam
     reference asks Ipopt to do) on a bounded sample: `nodes` node problems x K_s histogram rows."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import c_oracle
+    c_oracle.set_threads(os.cpu_count() or 1)      # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     t0 = time.time()
     _, info = c_oracle.learn_pairwise_packed(counts_sample, spins_sample, "RISE", lam, False, "exact", 1e-9,
                                              nodes=nodes, return_info=True)
@@ -150,6 +151,7 @@ def run_reference(args):
     lam = 0.4 * np.sqrt(np.log(n * n / 0.05) / args.nsamples)
     sys.path.insert(0, str(ROOT / "oracle"))
     import c_oracle
+    c_oracle.set_threads(os.cpu_count() or 1)
     nodes = (0, min(n, c_oracle.num_threads() * args.cpu_nodes_per_core))
     times, last = [], None
     for step in range(args.warmup + args.steps):
@@ -295,9 +297,10 @@ def run_b200(args):
                "learn_seconds": float(np.mean(e_times)), "steps": len(e_times)}
 
     cpu = None
-    if rank == 0 and not args.skip_cpu:
+    if rank == 0 and world == 1 and not args.skip_cpu:      # reported at N=1 only
         sys.path.insert(0, str(ROOT / "oracle"))
         import c_oracle
+        c_oracle.set_threads(os.cpu_count() or 1)
         ks = args.cpu_rows
         src = h_spins if not args.skip_e2e else spins.cpu()
         sample = np.ascontiguousarray(src[:, :ks].numpy())

@@ -24,6 +24,7 @@ EXPORTS = (
     "gml_b200_solve_pairwise_device", "gml_b200_solve_multibody", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
     "gml_b200_symmetrize_device",
     "gml_b200_sample_gibbs_device", "gml_b200_build_histogram_device",
+    "gml_b200_comm_unique_id", "gml_b200_comm_init", "gml_b200_comm_globalize_histogram",
 )
 
 
@@ -101,6 +102,9 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
                                                  c.c_uint64, vp, c.c_int64, vp]
     lib.gml_b200_build_histogram_device.argtypes = [c.c_int32, vp, c.c_int64, c.c_int32, c.c_int64, vp, c.c_int64, vp,
                                                     c.POINTER(c.c_int64), vp]
+    lib.gml_b200_comm_unique_id.argtypes = [vp]
+    lib.gml_b200_comm_init.argtypes = [vp, vp, c.c_int32, c.c_int32]
+    lib.gml_b200_comm_globalize_histogram.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is c.c_int and name not in ("gml_b200_device_count",):

@@ -82,6 +82,7 @@ class B200(GMLMethod):
     verbose: int = 0
     profile: bool = False         # time the contraction kernels with CUDA events (stats energy_*_ms / grad_ms)
     multilevel: bool = False      # FISTA: solve on strided sample subsets first (warm starts); opt-in
+    sample_sharded: bool = False  # histogram rows split over ranks, NCCL all-reduce per pass (Session.comm_init)
     last_stats: dict = field(default_factory=dict, repr=False, compare=False)
 
     def _opts(self, node_begin: int = 0, node_end: int = 0, stream: int = 0) -> _lib.Opts:
@@ -96,6 +97,7 @@ class B200(GMLMethod):
         o.stream = ctypes.c_void_p(stream) if stream else None
         o.reserved[0] = 1 if self.profile else 0
         o.reserved[1] = 1 if self.multilevel else 0
+        o.reserved[2] = 1 if self.sample_sharded else 0
         return o
 
 
@@ -355,3 +357,21 @@ class Session:
         opts = B200(solver=backend)._opts(node_begin, node_end)
         _lib.check(self._lib.gml_b200_bench_passes(self._h, form_id, ctypes.byref(opts), reps, _ptr(out)))
         return dict(zip(("energy_full", "grad", "energy_obj", "full_pass_wall"), out.tolist()))
+
+    # ---- sample-sharded mode -------------------------------------------------------------------------
+    def comm_init(self, group=None):
+        """Create the library's NCCL communicator over the ranks of a torch.distributed group (the 128-byte
+        unique id travels through torch.distributed), then make the resident histogram slice global."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = (ctypes.c_uint8 * 128)()
+        if rank == 0:
+            _lib.check(self._lib.gml_b200_comm_unique_id(ident))
+        dev = f"cuda:{self.device}" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (ctypes.c_uint8 * 128)(*t.cpu().tolist())
+        _lib.check(self._lib.gml_b200_comm_init(self._h, ident, rank, world))
+        _lib.check(self._lib.gml_b200_comm_globalize_histogram(self._h))
+        return self

@@ -119,6 +119,7 @@ struct gml_b200_handle {
     cudaStream_t own_stream = nullptr;
     Histogram hist;
     bool has_hist = false;
+    Comm* comm = nullptr;      // sample-sharded mode
 };
 
 namespace {
@@ -168,6 +169,13 @@ void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, con
     NodeProblem p;
     p.hist = &hist; p.Q = hist.base.p; p.F = N + 1; p.Fp = hist.Fb;
     p.form = formulation; p.lambda = lambda; p.Nn = ne - nb;
+    if (o.reserved[2] != 0) {
+        GML_REQUIRE(h->comm != nullptr, "sample-sharded solve needs gml_b200_comm_init first");
+        GML_REQUIRE(hist.M_local > 0.0, "sample-sharded solve needs gml_b200_comm_globalize_histogram after the upload");
+        GML_REQUIRE(o.solver == GML_B200_SOLVER_FISTA_TC || (o.solver == GML_B200_SOLVER_AUTO && p.F > NEWTON_MAX_F),
+                    "sample-sharded mode is implemented for the tensor-core FISTA solver");
+        p.comm = h->comm;
+    }
     p.spin_row.alloc(p.Nn); p.pen.alloc((size_t)p.Nn * p.Fp);
     EventTimer timer(st);
     pairwise_setup_kernel<<<p.Nn, 128, 0, st>>>(N, p.Fp, nb, p.Nn, p.spin_row.p, p.pen.p);
@@ -289,6 +297,7 @@ int gml_b200_create(gml_b200_handle** out, int32_t device) {
 void gml_b200_destroy(gml_b200_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    comm_destroy(h->comm);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -613,6 +622,32 @@ int gml_b200_build_histogram_device(int32_t device, const int8_t* d_samples, int
         GML_REQUIRE(ld >= M, "ld must be >= M");
         GML_CUDA(cudaSetDevice(device));
         *out_K = build_histogram(d_samples, M, N, ld, d_out_spins, ld_out, d_out_counts, (cudaStream_t)stream);
+    });
+}
+
+int gml_b200_comm_unique_id(uint8_t* out128) {
+    return guarded([&] {
+        GML_REQUIRE(out128 != nullptr, "null argument");
+        comm_unique_id(out128);
+    });
+}
+
+int gml_b200_comm_init(gml_b200_handle* h, const uint8_t* id128, int32_t rank, int32_t world) {
+    return guarded([&] {
+        GML_REQUIRE(h && id128, "null argument");
+        GML_CUDA(cudaSetDevice(h->device));
+        comm_destroy(h->comm);
+        h->comm = nullptr;
+        h->comm = comm_create(id128, rank, world);
+    });
+}
+
+int gml_b200_comm_globalize_histogram(gml_b200_handle* h) {
+    return guarded([&] {
+        GML_REQUIRE(h && h->has_hist && h->comm, "needs a resident histogram and gml_b200_comm_init");
+        GML_CUDA(cudaSetDevice(h->device));
+        comm_globalize_histogram(h->comm, h->hist, h->own_stream);
+        GML_CUDA(cudaStreamSynchronize(h->own_stream));
     });
 }
 

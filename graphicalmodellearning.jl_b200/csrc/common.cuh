@@ -77,7 +77,8 @@ struct Histogram {
     int64_t K = 0, Kp = 0;
     int32_t N = 0;           // spins
     int32_t Fb = 0;          // padded rows of `base`
-    double M = 0.0;          // sum of counts (num_samples of data_info)
+    double M = 0.0;          // sum of counts (num_samples of data_info); global after comm_globalize_histogram
+    double M_local = 0.0;    // this rank's share in sample-sharded mode (0 = not sharded)
     double wmax = 0.0;       // max_k c_k / M
     DevBuf<int8_t> base;
     DevBuf<double> w64;      // [Kp] c_k / M
@@ -92,8 +93,11 @@ struct Histogram {
 
 // One batched solve: Nn node problems over a shared +-1 feature matrix Q [Fp x Kp].
 //   minimise over x_u:  sum_k w_k g( s_u[k] * sum_f Q[f,k] x_u[f] ) + lambda * sum_{pen==L1} |x_u[f]|
+struct Comm;
+
 struct NodeProblem {
     Histogram* hist = nullptr;
+    Comm* comm = nullptr;           // sample-sharded mode: partial sums are all-reduced over this communicator
     const int8_t* Q = nullptr;      // feature matrix (hist->base or hist->mb)
     int32_t F = 0, Fp = 0;
     int32_t form = 0;
@@ -159,6 +163,16 @@ void symmetrize_rowmajor(double* d_theta, int N, cudaStream_t st);
 // --- histogram.cu : raw samples -> deduplicated histogram (returns the number of distinct configurations)
 int64_t build_histogram(const int8_t* d_samples, int64_t M, int N, int64_t ld, int8_t* d_out_spins, int64_t ld_out,
                         double* d_out_counts, cudaStream_t st);
+
+// --- comm.cu : NCCL plumbing of the sample-sharded mode
+void comm_unique_id(uint8_t* out128);
+Comm* comm_create(const uint8_t* id128, int rank, int world);
+void comm_destroy(Comm* c);
+int comm_world(const Comm* c);
+void comm_allreduce_sum_i64(Comm* c, long long* buf, size_t n, cudaStream_t st);
+void comm_allreduce_sum_f64(Comm* c, double* buf, size_t n, cudaStream_t st);
+void comm_allreduce_max_f64(Comm* c, double* buf, size_t n, cudaStream_t st);
+void comm_globalize_histogram(Comm* c, Histogram& h, cudaStream_t st);
 
 // --- sampler.cu
 void sample_gibbs(int N, const int32_t* d_row_ptr, const int32_t* d_col, const float* d_J, const float* d_h,

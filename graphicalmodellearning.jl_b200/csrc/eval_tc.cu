@@ -769,6 +769,10 @@ struct BackendTC : EvalBackend {
             GML_LAUNCHED();
             span_end(st);
         }
+        if (p.comm) {   // sample-sharded: exact int64 gradient sums and fp64 objective sums across the ranks
+            comm_allreduce_sum_f64(p.comm, fsum.p, Nn_pad1, st);
+            if (want_grad) comm_allreduce_sum_i64(p.comm, G64.p, (size_t)Nn_pad2 * p.Fp, st);
+        }
         tc_finalize_kernel<<<p.Nn, 128, 0, st>>>(p.form, p.Nn, p.Fp, fsum.p, G64.p, delta.p, f_out, g_out, want_grad ? 1 : 0);
         GML_LAUNCHED();
     }

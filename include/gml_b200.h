@@ -56,7 +56,8 @@ typedef struct gml_b200_opts {
     int32_t verbose;
     void* stream;       /* cudaStream_t to launch on; NULL = the handle's own stream */
     int32_t reserved[8]; /* reserved[0] != 0: time the contraction kernels with CUDA events (stats.reserved_d);
-                            reserved[1] != 0: enable the multilevel (sample-subset) continuation of the FISTA solvers */
+                            reserved[1] != 0: enable the multilevel (sample-subset) continuation of the FISTA solvers;
+                            reserved[2] != 0: sample-sharded solve (see gml_b200_comm_init) */
 } gml_b200_opts;
 
 typedef struct gml_b200_stats {
@@ -160,6 +161,16 @@ int gml_b200_symmetrize_device(double* d_theta, int32_t N, void* stream);
 int gml_b200_sample_gibbs_device(int32_t device, int32_t N, const int32_t* row_ptr, const int32_t* col_idx,
                                  const float* coupling, const float* field, int64_t n_samples,
                                  int32_t sweeps, uint64_t seed, int8_t* d_spins, int64_t ld, void* stream);
+
+/* ---- sample-sharded mode: histogram rows split over ranks, every rank solves all nodes; per pass
+ * the int64 gradient sums and fp64 objective sums are combined with NCCL all-reduces on the solve stream.
+ *   rank 0: gml_b200_comm_unique_id(id) -> broadcast the 128 bytes with any transport -> every rank:
+ *   gml_b200_comm_init(h, id, rank, world); upload the rank's slice; gml_b200_comm_globalize_histogram(h)
+ *   (global M and weights); then solve with opts->reserved[2] = 1.  lambda must be computed from the GLOBAL
+ *   sample count (gml_b200_num_samples after the globalize call). */
+int gml_b200_comm_unique_id(uint8_t* out128);
+int gml_b200_comm_init(gml_b200_handle* h, const uint8_t* id128, int32_t rank, int32_t world);
+int gml_b200_comm_globalize_histogram(gml_b200_handle* h);
 
 /* ---- histogram builder: replaces the host `countmap` of src/sampling.jl:52-54 -----------------
  * d_samples: M raw samples, int8 spin-major [N x ld] in device memory, N <= 64.  Writes the K distinct

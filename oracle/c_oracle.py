@@ -111,5 +111,9 @@ def learn_multibody(samples, regularizer=0.4, symmetrization=True, interaction_o
     return recon
 
 
+def set_threads(n: int) -> None:
+    lib().gml_oracle_set_threads(ctypes.c_int(int(n)))
+
+
 def num_threads() -> int:
     return int(lib().gml_oracle_num_threads())

@@ -375,6 +375,15 @@ int gml_oracle_learn_multibody(const double* counts, const int8_t* spins, int64_
     return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline asks for the host cores explicitly */
+void gml_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int gml_oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

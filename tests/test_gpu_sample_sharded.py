@@ -1,0 +1,57 @@
+"""Sample-sharded mode: histogram rows split over 2 GPUs, NCCL all-reduce of the exact int64 gradient
+sums per pass; must reproduce the single-GPU solution.  Needs two GPUs (skipped otherwise)."""
+import os
+import pathlib
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, counts, spins, expected, q):
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    import gml_b200
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    k = spins.shape[1]
+    lo, hi = k * rank // world, k * (rank + 1) // world
+    sess = gml_b200.Session(rank).upload(np.ascontiguousarray(counts[lo:hi]), np.ascontiguousarray(spins[:, lo:hi]))
+    sess.comm_init()
+    assert abs(sess.num_samples - counts.sum()) < 1e-6          # global M after the globalize step
+    m = gml_b200.B200(solver="fista_tc", sample_sharded=True, device=rank)
+    got = sess.solve_pairwise(gml_b200.RISE(0.4, False), m)
+    q.put((rank, float(np.abs(got - expected).max()), m.last_stats["iterations"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sample_sharded_matches_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    for p in (ROOT, ROOT / "oracle", ROOT / "tests"):
+        sys.path.insert(0, str(p))
+    import gml_b200
+    from helpers import histogram_c1
+    _, hist = histogram_c1(n=16, m_samples=300_000, seed=16)
+    counts, spins = gml_b200.pack_histogram(hist)
+    expected = gml_b200.learn(hist, gml_b200.RISE(0.4, False), gml_b200.B200(solver="fista_tc"))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, counts, spins, expected, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, iters in results:
+        assert err <= 1e-7, (rank, err)
