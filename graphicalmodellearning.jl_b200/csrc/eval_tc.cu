@@ -8,7 +8,8 @@
 //     is then four int8 GEMM column groups with int32 accumulation -- no rounding at all.
 //   * the epilogue turns E into t = s_u E, psi = exp(-t) (or the RPLE logistic terms) in fp32, and
 //     quantises  r = s_u w psi  to nR balanced int8 limbs with a per-node scale derived from the
-//     bound |t| <= |x_u|_1; the objective term is accumulated as an int64 sum of the same grid.
+//     bound |t| <= |x_u|_1; the objective terms are summed in fp32 per thread over <= 32 sample blocks
+//     and then in fp64.
 //   * the gradient contraction  G[u,f] = -sum_k r[u,k] S[k,f]  is again an int8 GEMM, split over
 //     sample ranges; partial tiles are combined with int64 atomics, so the result is independent
 //     of the reduction order (bitwise reproducible).

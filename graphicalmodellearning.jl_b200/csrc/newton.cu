@@ -416,16 +416,6 @@ __global__ void newton_update_kernel(NewtonParams p, int form, int n_alpha) {
     }
 }
 
-__global__ void count_active_kernel(const int* conv, int Nn, int* n_active) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < Nn && conv[u] != 1) atomicAdd(n_active, 1);
-}
-
-template <class T> __global__ void fill_kernel(T* p, int64_t n, T v) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
 void launch_accum(const NewtonParams& P, int form, cudaStream_t st) {
     const int Ptot = P.F + P.F * (P.F + 1) / 2;
     const int ne = (int)ceil_div(Ptot, NT);

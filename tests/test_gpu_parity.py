@@ -186,3 +186,29 @@ def test_edge_cases(golden):
     with pytest.raises(gml_b200.GMLB200Error) as e:
         gml_b200.learn(hist, RISE(), B200(solver="fista_cc", max_iter=2))
     assert e.value.code == 3
+
+
+@pytest.mark.parametrize("form", list(FORMS))
+@pytest.mark.parametrize("backend", ["fista_cc", "fista_tc"])
+def test_contraction_kernels_vs_oracle_gradient(form, backend):
+    """Objective and gradient passes (K2/K3) at a dense random point against the float64 restatement of
+    src/GraphicalModelLearning.jl:170/279/317 (N=40: 41 features -> one 128-wide feature block, ragged node tile)."""
+    n = 40
+    rng = np.random.default_rng(3)
+    spins = rng.choice(np.array([-1, 1], dtype=np.int8), size=(n, 30_001))       # K not a multiple of 128
+    counts = rng.integers(1, 5, size=30_001).astype(np.float64)
+    hist = np.concatenate([counts[:, None], spins.T.astype(np.float64)], axis=1)
+    w = counts / counts.sum()
+    x = rng.normal(size=(n, n + 1)) * 0.1 * (rng.random((n, n + 1)) < 0.3)
+    x = np.round(x * 2 ** 24) / 2 ** 24
+    x[np.arange(n), np.arange(n)] = 0.0
+    sess = gml_b200.Session().upload(counts, np.ascontiguousarray(spins))
+    f, g = sess.eval_pairwise(FORMS[form](), x, backend)
+    fr = np.zeros(n); gr = np.zeros((n, n + 1))
+    for u in range(n):
+        stat = o.nodal_stat_pairwise(hist, u)
+        xv = x[u, :n].copy(); xv[u] = x[u, n]
+        fu, gu, _ = o.smooth_parts(form, xv, stat, w, hess=False)
+        fr[u] = fu; gr[u, :n] = gu; gr[u, n] = gu[u]; gr[u, u] = 0.0
+    assert np.abs(f - fr).max() <= 2e-6 * max(1.0, np.abs(fr).max())
+    assert np.abs(g - gr).max() <= 2e-5 * max(1.0, np.abs(gr).max())
