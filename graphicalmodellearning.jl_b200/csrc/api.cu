@@ -334,15 +334,18 @@ int gml_b200_upload_histogram(gml_b200_handle* h, const double* counts, const in
         GML_CUDA(cudaSetDevice(h->device));
         cudaStream_t st = h->own_stream;
         DevBuf<double> dc;
-        DevBuf<int8_t> ds;
         dc.alloc(K);
-        ds.alloc((size_t)N * K);
+        // the spins land directly in their final place (rows of `base`, pitch Kp); validation and padding
+        // then run in place -- no staging copy of the histogram on the device
+        Histogram& hist = h->hist;
+        const int64_t Kp = round_up(K, KPAD);
+        hist.base.alloc((size_t)round_up(N + 1, FPAD) * Kp);
         EventTimer timer(st);
         GML_CUDA(cudaMemcpyAsync(dc.p, counts, sizeof(double) * K, cudaMemcpyHostToDevice, st));
-        GML_CUDA(cudaMemcpy2DAsync(ds.p, K, spins, ld, K, N, cudaMemcpyHostToDevice, st));
+        GML_CUDA(cudaMemcpy2DAsync(hist.base.p, Kp, spins, ld, K, N, cudaMemcpyHostToDevice, st));
         const double h2d = timer.stop();
         gml_b200_stats tmp;
-        const int rc = gml_b200_attach_histogram_device(h, dc.p, ds.p, K, N, K, &tmp);
+        const int rc = gml_b200_attach_histogram_device(h, dc.p, hist.base.p, K, N, Kp, &tmp);
         if (rc != GML_B200_OK) throw CudaError{rc};
         if (stats) {
             *stats = tmp;

@@ -53,3 +53,31 @@ def learn_sharded(session, formulation, method, symmetrize: bool = True, group=N
         _lib.check(_lib.load().gml_b200_symmetrize_device(ctypes.c_void_p(full.data_ptr()), n,
                                                           ctypes.c_void_p(stream)))
     return full
+
+
+def upload_replicated(session, counts, spins, group=None):
+    """Make the full histogram resident on every rank with ONE pass over the host link per byte: each rank
+    copies only its 1/world block of spin rows host->device, the blocks are exchanged with an NCCL
+    all-gather over NVLink, and the library packs the result.  `counts` (f64 [K]) and `spins` (int8 [N x K],
+    spin-major) are host arrays (pinned for full H2D speed) holding the same data on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    # torch tensors keep their pinned-memory attribute (numpy views of pinned memory are copied as pageable)
+    t_spins = spins if isinstance(spins, torch.Tensor) else torch.from_numpy(spins)
+    t_counts = counts if isinstance(counts, torch.Tensor) else torch.from_numpy(counts)
+    if world == 1:
+        return session.upload(t_counts.numpy(), t_spins.numpy())
+    n, k = t_spins.shape
+    # Split by SPIN ROWS: in the spin-major layout a block of rows is one contiguous host range (full-speed
+    # H2D, no strided copy), and the all-gather along dim 0 reassembles [N x K] directly.
+    rows = -(-n // world)
+    dev = torch.device(f"cuda:{session.device}")
+    lo, hi = min(n, rank * rows), min(n, (rank + 1) * rows)
+    part = torch.ones((rows, k), dtype=torch.int8, device=dev)
+    part[: hi - lo].copy_(t_spins[lo:hi], non_blocking=True)
+    full = torch.empty((world * rows, k), dtype=torch.int8, device=dev)
+    dist.all_gather_into_tensor(full, part, group=group)
+    d_counts = t_counts.to(dev, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    session.attach_device(d_counts.data_ptr(), full.data_ptr(), k, n, k)
+    return session
