@@ -254,11 +254,15 @@ def run_b200(args):
     dom = max(ker, key=lambda kk: ker[kk][0])
     peak_tf, peak_gbs, peak_src = load_peaks()
     roof = None
+    traffic = None
+    tfile = ROOT / "profiles" / "r1_traffic.json"
+    if tfile.exists() and world == 1 and n == 1000 and k == 10_000_000:
+        traffic = json.loads(tfile.read_text()).get("c3_1gpu", {}).get(dom)      # from the committed ncu --set full capture
     if ker[dom][0] > 0:
         avg_ms = ker[dom][0] / max(1, ker[dom][1])
         ach = flops_per_launch / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "avg_launch_ms": avg_ms, "launches": ker[dom][1], "peak_source": peak_src,
+                "traffic": traffic, "avg_launch_ms": avg_ms, "launches": ker[dom][1], "peak_source": peak_src,
                 "algorithmic_flops_per_launch": flops_per_launch,
                 "kernel_ms_share": {kk: v[0] / stats["solve_ms"] for kk, v in ker.items()},
                 "note": "algorithmic flops (2*K*F*nodes per contraction); the int8 limb split executes 4x (energy) / "
@@ -316,10 +320,11 @@ def run_b200(args):
     if rank == 0:
         line = {"metric": "node_sample_evals_per_s", "value": value, "unit": "node*sample evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "int8 tensor-core contractions (s32 accumulate) + f32 epilogue, f64 solver state",
+                "scaling": "strong", "vs_baseline": None, "dtype": "int8",
                 "data": "synthetic",
                 "config": {"workload": f"C3: learn() RISE(0.4,true), N={n} random 4-regular Ising J=+-0.4, M=K={k:g} Gibbs samples "
                                        f"({args.sweeps} sweeps/chain), node-sharded over {world} GPU(s), histogram replicated",
+                           "arithmetic": "int8 tensor-core contractions with s32/s64 accumulation (exact), f32 per-sample epilogue, f64 solver state",
                            "tol": args.tol, "solver": args.solver, "l2_note": "inputs (10 GB int8 + 30 GB residual limbs) exceed the 126 MB L2",
                            "lambda": lam, "sampler_seconds": gen_s},
                 "learn_seconds": ms_step * 1e-3, "passes": {"fg": stats["n_fg_passes"], "f": stats["n_f_passes"], "iterations": stats["iterations"]},

@@ -21,7 +21,7 @@ EXPORTS = (
     "gml_b200_learn_pairwise", "gml_b200_learn_multibody", "gml_b200_multibody_num_keys",
     "gml_b200_create", "gml_b200_destroy", "gml_b200_upload_histogram",
     "gml_b200_attach_histogram_device", "gml_b200_num_samples", "gml_b200_solve_pairwise",
-    "gml_b200_solve_pairwise_device", "gml_b200_solve_multibody", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
+    "gml_b200_solve_pairwise_device", "gml_b200_solve_pairwise_path", "gml_b200_solve_multibody", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
     "gml_b200_symmetrize_device",
     "gml_b200_sample_gibbs_device", "gml_b200_build_histogram_device",
     "gml_b200_comm_unique_id", "gml_b200_comm_init", "gml_b200_comm_globalize_histogram",
@@ -94,6 +94,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gml_b200_num_samples.restype = c.c_double
     lib.gml_b200_solve_pairwise.argtypes = [vp, c.c_int32, c.c_double, c.c_int32, op, vp, vp, sp]
     lib.gml_b200_solve_pairwise_device.argtypes = [vp, c.c_int32, c.c_double, op, vp, vp, sp]
+    lib.gml_b200_solve_pairwise_path.argtypes = [vp, c.c_int32, vp, c.c_int32, c.c_int32, op, vp, sp]
     lib.gml_b200_solve_multibody.argtypes = [vp, c.c_int32, c.c_double, op, vp, vp, sp]
     lib.gml_b200_eval_pairwise.argtypes = [vp, c.c_int32, op, vp, vp, vp]
     lib.gml_b200_bench_passes.argtypes = [vp, c.c_int32, op, c.c_int32, vp]

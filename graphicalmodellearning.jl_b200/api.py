@@ -375,3 +375,19 @@ class Session:
         _lib.check(self._lib.gml_b200_comm_init(self._h, ident, rank, world))
         _lib.check(self._lib.gml_b200_comm_globalize_histogram(self._h))
         return self
+
+    def solve_path(self, formulation, method: B200, regularizers):
+        """Regularisation path: one solve per regulariser c (lambda = c*sqrt(log(N^2/0.05)/M), :157), each warm
+        started from the previous one.  Returns an array [len(regularizers), N, N]."""
+        N = self.N
+        form_id = {RISE: 0, logRISE: 1, RPLE: 2}[type(formulation)]
+        lams = np.array([regularizer_lambda(c, N, self.num_samples) for c in regularizers], dtype=np.float64)
+        out = np.zeros((len(lams), N, N))
+        st = _lib.Stats()
+        opts = method._opts()
+        rc = self._lib.gml_b200_solve_pairwise_path(self._h, form_id, _ptr(lams), len(lams),
+                                                    int(bool(formulation.symmetrization)), ctypes.byref(opts), _ptr(out),
+                                                    ctypes.byref(st))
+        method.last_stats = st.as_dict()
+        _lib.check(rc)
+        return np.ascontiguousarray(out.transpose(0, 2, 1))      # column-major slices -> row-major numpy

@@ -159,7 +159,8 @@ void finish_stats(gml_b200_stats* stats, const SolveResult& r, int solver_used, 
 }
 
 void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, const gml_b200_opts& o, int nb, int ne,
-                         double* d_rows, double* d_obj, gml_b200_stats* stats, cudaStream_t st, double t0) {
+                         double* d_rows, double* d_obj, gml_b200_stats* stats, cudaStream_t st, double t0,
+                         DevBuf<double>* warm = nullptr /* in: start point (if allocated), out: solution [Nn x Fp] */) {
     GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
     GML_REQUIRE(formulation >= GML_B200_RISE && formulation <= GML_B200_RPLE, "unknown formulation id");
     GML_REQUIRE(lambda >= 0.0 && std::isfinite(lambda), "lambda must be finite and >= 0");
@@ -182,10 +183,15 @@ void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, con
     GML_LAUNCHED();
     SolveResult r;
     int solver_used = 0;
+    if (warm && warm->p) p.x0 = warm->p;
     run_solver(p, o, r, solver_used, st);
     pairwise_rows_kernel<<<p.Nn, 128, 0, st>>>(r.x.p, N, p.Fp, nb, d_rows);
     GML_LAUNCHED();
     if (d_obj) GML_CUDA(cudaMemcpyAsync(d_obj, r.objective.p, sizeof(double) * p.Nn, cudaMemcpyDeviceToDevice, st));
+    if (warm) {
+        warm->alloc((size_t)p.Nn * p.Fp);
+        GML_CUDA(cudaMemcpyAsync(warm->p, r.x.p, sizeof(double) * p.Nn * p.Fp, cudaMemcpyDeviceToDevice, st));
+    }
     const double solve_ms = timer.stop();
     finish_stats(stats, r, solver_used, p.Nn, hist.K, solve_ms, 0.0, t0);
     if (r.n_unconverged > 0) {
@@ -407,6 +413,45 @@ int gml_b200_solve_pairwise(gml_b200_handle* h, int32_t formulation, double lamb
             for (int i = 0; i < N; ++i) out_theta[(size_t)(nb + u) + (size_t)N * i] = hrows[(size_t)u * N + i];
         if (stats) { stats->d2h_ms = d2h; stats->kernel_launches = g_launches; stats->total_ms = now_ms() - t0; }
         if (rc != GML_B200_OK) throw CudaError{rc};
+    });
+}
+
+int gml_b200_solve_pairwise_path(gml_b200_handle* h, int32_t formulation, const double* lambdas, int32_t n_lambda,
+                                 int32_t symmetrize, const gml_b200_opts* opts, double* out_thetas, gml_b200_stats* stats) {
+    return guarded([&] {
+        GML_REQUIRE(h && lambdas && out_thetas && n_lambda >= 1, "bad argument");
+        GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
+        const double t0 = now_ms();
+        g_launches = 0;
+        gml_b200_opts o; fill_opts(o, opts);
+        GML_CUDA(cudaSetDevice(h->device));
+        cudaStream_t st = stream_of(h, o);
+        const int N = h->hist.N;
+        GML_REQUIRE(pick_solver(o, N + 1) != GML_B200_SOLVER_NEWTON, "the regularisation path uses the FISTA solvers (set opts->solver)");
+        DevBuf<double> rows, warm;
+        rows.alloc((size_t)N * N);
+        std::vector<double> hrows((size_t)N * N);
+        gml_b200_stats acc{}, cur{};
+        for (int li = 0; li < n_lambda; ++li) {
+            std::memset(&cur, 0, sizeof(cur));
+            solve_pairwise_rows(h, formulation, lambdas[li], o, 0, N, rows.p, nullptr, &cur, st, now_ms(), &warm);   // warm start
+            if (symmetrize) {
+                dim3 b(32, 8), g((unsigned)ceil_div(N, 32), (unsigned)ceil_div(N, 8));
+                symmetrize_kernel<<<g, b, 0, st>>>(rows.p, N);
+                GML_LAUNCHED();
+            }
+            GML_CUDA(cudaMemcpyAsync(hrows.data(), rows.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
+            GML_CUDA(cudaStreamSynchronize(st));
+            double* out = out_thetas + (size_t)li * N * N;
+            for (int u = 0; u < N; ++u)
+                for (int i = 0; i < N; ++i) out[(size_t)u + (size_t)N * i] = hrows[(size_t)u * N + i];
+            acc.iterations += cur.iterations; acc.n_fg_passes += cur.n_fg_passes; acc.n_f_passes += cur.n_f_passes;
+            acc.evals += cur.evals; acc.solve_ms += cur.solve_ms; acc.solver_used = cur.solver_used;
+            acc.max_residual = std::max(acc.max_residual, cur.max_residual);
+        }
+        acc.kernel_launches = g_launches;
+        acc.total_ms = now_ms() - t0;
+        if (stats) *stats = acc;
     });
 }
 

@@ -105,6 +105,7 @@ struct NodeProblem {
     int32_t Nn = 0;                 // nodes in this shard
     DevBuf<int32_t> spin_row;       // [Nn] row of hist->base that holds s_u
     DevBuf<uint8_t> pen;            // [Nn x Fp] penalty class per coordinate (padded features = PEN_ZERO)
+    const double* x0 = nullptr;     // optional warm start [Nn x Fp] (FISTA solvers; e.g. the previous point of a lambda path)
 };
 
 struct SolveResult {

@@ -24,7 +24,7 @@ namespace {
 
 struct FistaState {
     int Nn, Fp, form;
-    double lambda, tol, lattice_inv, lattice, eps_f;
+    double lambda, tol, lattice_inv, lattice, eps_f, eps_g;
     const uint8_t* pen;
     double *X, *Z, *Y, *Yn, *G, *Gn;
     double *fY, *fYn, *L, *t, *tn, *q, *c, *gmap, *obj;
@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
     const int64_t o = (int64_t)u * s.Fp;
     const double gm = s.gmap[u];
     // ---- convergence is decided at Y (whose gradient is known): the prox point Z is the answer
-    if (gm <= s.tol) {
+    // (on a lattice backend a prox step of at most one lattice unit is the finest resolvable fixed point)
+    if (gm <= s.tol || (s.lattice > 0.0 && gm <= 1.01 * s.L[u] * s.lattice)) {
         for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) s.X[o + f] = s.Z[o + f];
         if (threadIdx.x == 0) s.status[u] = 1;
         return;
@@ -118,13 +119,20 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
     // absolute for logRISE (f = log Z).  D is the slack of the descent test; for a locally quadratic f,
     // D/c = 1 - L_dir/L with L_dir the curvature along Y' - Y.
     const double noise = s.eps_f * (s.form == GML_B200_LOGRISE ? fmax(fabs(fY), 1.0) : fmax(fabs(fY), 1e-300));
-    const double c = s.c[u], D = fY + s.q[u] - fN;
+    const double c = s.c[u];
     const bool measurable = c > 10.0 * noise;
-    // Reject only a violation that is significant against both the noise and c (L more than ~10% below
-    // the directional curvature).  Steps inside the noise floor cannot be verified: they keep the L
-    // validated by the larger steps before them; should such an L be too small the steps grow until
-    // the test is measurable again.
-    const bool reject = !isfinite(fN) || (measurable && D < -(0.1 * c + noise));
+    // Inside the noise floor of f the same curvature is read from the GRADIENTS, which stay accurate for tiny
+    // steps: <G' - G, Y' - Y> = dY^T H dY, so D = c (1 - L_dir / L) with L_dir = <G'-G, dY> / |dY|^2.
+    __shared__ double red[4];
+    double dot = 0.0;
+    for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) dot += (s.Gn[o + f] - s.G[o + f]) * (s.Yn[o + f] - s.Y[o + f]);
+    dot = block_sum(dot, red);
+    // ... as long as the gradient change L|dY| is well above the gradient noise of the backend
+    const bool secant_ok = !measurable && s.L[u] * sqrt(2.0 * c / s.L[u]) > 20.0 * s.eps_g;
+    const double D = measurable ? fY + s.q[u] - fN : (secant_ok ? c - 0.5 * dot : 0.0);
+    // Reject only a violation that is significant against c (L more than ~10% below the directional
+    // curvature) and, for the function-value form, against the noise.
+    const bool reject = !isfinite(fN) || !isfinite(dot) || (c > 0.0 && D < -(0.1 * c + (measurable ? noise : 0.0)));
     if (reject) {
         if (threadIdx.x == 0) { s.L[u] *= 2.0; s.streak[u] = 0; atomicAdd(s.n_active, 1); }
         return;
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
         // L is relaxed after three consecutive measurable steps that passed with L > 1.33 L_dir, so it
         // tracks the local curvature (which drops along the path for RPLE) within [0.9, 1.33] L_dir
         int streak = s.streak[u];
-        if (measurable) streak = (D > 0.25 * c) ? streak + 1 : 0;
+        streak = (c > 0.0 && D > 0.25 * c) ? streak + 1 : 0;
         if (streak >= 3) { s.L[u] *= 0.85; streak = 0; }
         s.streak[u] = streak;
         if (stalled) s.status[u] = 2; else atomicAdd(s.n_active, 1);
@@ -188,7 +196,8 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     Z.alloc(nx); Y.alloc(nx); Yn.alloc(nx); G.alloc(nx); Gn.alloc(nx);
     fY.alloc(Nn); fYn.alloc(Nn); L.alloc(Nn); t.alloc(Nn); tn.alloc(Nn); q.alloc(Nn); c.alloc(Nn); gmap.alloc(Nn);
     status.alloc(Nn); n_active.alloc(1); best.alloc(Nn); stall.alloc(Nn); streak.alloc(Nn);
-    GML_CUDA(cudaMemsetAsync(r.x.p, 0, nx * sizeof(double), st));
+    if (prob.x0) GML_CUDA(cudaMemcpyAsync(r.x.p, prob.x0, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    else GML_CUDA(cudaMemsetAsync(r.x.p, 0, nx * sizeof(double), st));
     GML_CUDA(cudaMemsetAsync(Y.p, 0, nx * sizeof(double), st));
     GML_CUDA(cudaMemsetAsync(Z.p, 0, nx * sizeof(double), st));
 
@@ -198,6 +207,7 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     s.lattice = be->lattice();
     s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
     s.eps_f = 1e-6;   // generous upper bound of the evaluation noise of f
+    s.eps_g = backend == GML_B200_SOLVER_FISTA_TC ? 1e-7 : 5e-6;   // absolute noise of a gradient component (per unit weight mass)
     s.best = best.p; s.stall = stall.p; s.streak = streak.p;
     s.pen = prob.pen.p;
     s.X = r.x.p; s.Z = Z.p; s.Y = Y.p; s.Yn = Yn.p; s.G = G.p; s.Gn = Gn.p;
@@ -232,6 +242,7 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
         const double scale = scale_free ? 1.0 : rho;
         // weights are not renormalised: f_level = rho * (normalised f), so lambda, L and the tolerance scale by rho
         s.lambda = prob.lambda * scale;
+        s.eps_g = (backend == GML_B200_SOLVER_FISTA_TC ? 1e-7 : 5e-6) * scale;
         s.tol = scale * (last ? user_tol : std::max(user_tol, 0.1 / std::sqrt(std::max(hist.M * rho, 1.0))));
         fista_init_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s, li == 0 ? scale : -(scale_free ? 1.0 : rho / rho_prev));
         GML_LAUNCHED();

@@ -134,6 +134,12 @@ int gml_b200_solve_pairwise(gml_b200_handle* h, int32_t formulation, double lamb
 int gml_b200_solve_pairwise_device(gml_b200_handle* h, int32_t formulation, double lambda,
                                    const gml_b200_opts* opts, double* d_out_rows, double* d_out_objective /* nullable */,
                                    gml_b200_stats* stats);
+/* Regularisation path: solves the same histogram for n_lambda values of lambda, each solve warm
+ * started from the previous solution (pass the lambdas in decreasing order).  out_thetas holds n_lambda
+ * consecutive N x N column-major matrices.  FISTA solvers only (opts->solver = FISTA_TC / FISTA_CC, or AUTO with
+ * more than 64 features). */
+int gml_b200_solve_pairwise_path(gml_b200_handle* h, int32_t formulation, const double* lambdas, int32_t n_lambda,
+                                 int32_t symmetrize, const gml_b200_opts* opts, double* out_thetas, gml_b200_stats* stats);
 int gml_b200_solve_multibody(gml_b200_handle* h, int32_t interaction_order, double lambda,
                              const gml_b200_opts* opts, double* out_vals, double* out_objective,
                              gml_b200_stats* stats);

@@ -137,3 +137,21 @@ def test_device_histogram_builder_and_sampler():
     hist = np.concatenate([out_counts[:K].cpu().numpy()[:, None], dev_spins.T.astype(np.float64)], axis=1)
     learned = gml_b200.learn(hist, RISE())
     assert np.abs(learned - model).max() <= 0.02
+
+
+def test_regularisation_path_warm_starts(c2_session):
+    """a lambda path with warm starts gives the same matrices as independent cold solves and needs
+    fewer passes for the later points."""
+    sess, _, _ = c2_session
+    cs = [0.8, 0.4, 0.2]
+    m = B200(solver="fista_tc")
+    path = sess.solve_path(RISE(0.4, True), m, cs)
+    warm_passes = m.last_stats["n_fg_passes"]
+    cold_passes = 0
+    for i, c in enumerate(cs):
+        mc = B200(solver="fista_tc")
+        cold = sess.solve_pairwise(RISE(c, True), mc)
+        cold_passes += mc.last_stats["n_fg_passes"]
+        assert np.abs(path[i] - cold).max() <= 5e-6
+    print("path passes warm", warm_passes, "cold", cold_passes)
+    assert warm_passes <= cold_passes + 2
