@@ -202,7 +202,7 @@ def run_b200(args):
     sess = gml_b200.Session(local).attach_device(counts.data_ptr(), spins.data_ptr(), k, n, k)
     form = gml_b200.RISE(0.4, True)
     lam = gml_b200.regularizer_lambda(0.4, n, float(k))
-    method = gml_b200.B200(solver=args.solver, tol=args.tol, device=local, profile=True, verbose=args.verbose, multilevel=args.multilevel)
+    method = gml_b200.B200(solver=args.solver, tol=args.tol, device=local, profile=True, verbose=args.verbose, multilevel=args.multilevel, coarse_level=not args.no_coarse)
     b, e = shard_bounds(n, world, rank)
 
     def barrier():
@@ -278,7 +278,7 @@ def run_b200(args):
         sess.close()
         torch.cuda.empty_cache()
         np_spins, np_counts = h_spins.numpy(), h_counts.numpy()
-        e2e_method = gml_b200.B200(solver=args.solver, tol=args.tol, device=local, multilevel=args.multilevel)
+        e2e_method = gml_b200.B200(solver=args.solver, tol=args.tol, device=local, multilevel=args.multilevel, coarse_level=not args.no_coarse)
         e_times = []
         for it in range(1 + args.e2e_steps):
             barrier()
@@ -355,6 +355,7 @@ def main():
     ap.add_argument("--cpu-nodes-per-core", type=int, default=1)
     ap.add_argument("--verbose", type=int, default=0)
     ap.add_argument("--multilevel", action="store_true")
+    ap.add_argument("--no-coarse", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

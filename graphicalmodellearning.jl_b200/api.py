@@ -83,6 +83,7 @@ class B200(GMLMethod):
     profile: bool = False         # time the contraction kernels with CUDA events (stats energy_*_ms / grad_ms)
     multilevel: bool = False      # FISTA: solve on strided sample subsets first (warm starts); opt-in
     sample_sharded: bool = False  # histogram rows split over ranks, NCCL all-reduce per pass (Session.comm_init)
+    coarse_level: bool = True     # fista_tc: 3-limb iterate / one residual limb less while far from convergence
     last_stats: dict = field(default_factory=dict, repr=False, compare=False)
 
     def _opts(self, node_begin: int = 0, node_end: int = 0, stream: int = 0) -> _lib.Opts:
@@ -98,6 +99,7 @@ class B200(GMLMethod):
         o.reserved[0] = 1 if self.profile else 0
         o.reserved[1] = 1 if self.multilevel else 0
         o.reserved[2] = 1 if self.sample_sharded else 0
+        o.reserved[3] = 0 if self.coarse_level else 1
         return o
 
 

@@ -146,6 +146,11 @@ struct EvalBackend {
     // [Nn x Fp] its gradient when want_grad.  lattice() > 0 means x must lie on that grid.
     virtual void eval(const double* x, bool want_grad, double* f_out, double* g_out, cudaStream_t st) = 0;
     virtual double lattice() const { return 0.0; }
+    // precision level of the following passes: 0 = coarse (cheaper, coarser lattice), 1 = fine.  Returns
+    // whether the requested level was taken (backends without levels always run fine).
+    virtual bool set_level(int lv, cudaStream_t) { return lv == 1; }
+    // estimated absolute noise of one gradient component at the current precision level (per unit weight mass)
+    virtual double grad_noise() const { return 5e-6; }
     // optional per-kernel device timing (opts.reserved[0] != 0): out[0] = energy-kernel ms (full passes),
     // out[1] = gradient-kernel ms, out[2] = energy-kernel ms (objective-only passes), out[3] = number of timed full passes
     // (only launches that sweep the whole histogram are timed)

@@ -117,8 +117,11 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
 // ------------------------------------------------------------------------------------------
 // fixed-point helpers
 // ------------------------------------------------------------------------------------------
-constexpr double X_LATTICE = 1.0 / 16777216.0;   // 2^-24
-constexpr int X_LIMBS = 4;
+// Two precision levels of the iterate:
+//   fine   : lattice 2^-24, |x| < 8, 4 limbs (28 bits)      -- final rounds
+//   coarse : lattice 2^-20, |x| < 1, 3 limbs (21 bits)      -- while the gradient mapping is >> the lattice
+constexpr double X_LATTICE_FINE = 1.0 / 16777216.0, X_LATTICE_COARSE = 1.0 / 1048576.0;
+constexpr int X_LIMBS_MAX = 4;
 constexpr int NODE_TILE1 = 64;                   // nodes per energy tile (4 limbs -> N = 256)
 constexpr int NODE_TILE2 = 128;                  // nodes per gradient tile (M = 128)
 
@@ -131,26 +134,28 @@ __device__ __forceinline__ int balanced_digit(int& q) {   // returns q mod 128 i
 }
 
 
-// x [Nn x Fp] (double, on the lattice) -> limb tiles X4 [(tile*4 + limb)*64 + i][Fp] and per-node scales
+// x [Nn x Fp] (double, on the lattice) -> limb tiles X [(tile*xl + limb)*64 + i][Fp] and per-node residual scales
 __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __restrict__ x, int Nn, int Fp, int form, double wmax,
-                                                           int nR, int8_t* __restrict__ X4, float* __restrict__ inv_dr,
-                                                           double* __restrict__ delta /* [Nn_pad]: deltaR */, int* __restrict__ flags) {
+                                                           int nR, int xl, double inv_lattice, int8_t* __restrict__ X,
+                                                           float* __restrict__ inv_dr, double* __restrict__ delta /* [Nn_pad]: deltaR */,
+                                                           int* __restrict__ flags) {
     const int u = blockIdx.x;
     const int tile = u / NODE_TILE1, i = u % NODE_TILE1;
     __shared__ double red[4];
+    // largest |q| that xl balanced base-128 digits can hold
+    const long long qcap = xl == 3 ? 1040000LL : 134000000LL;
     double l1 = 0.0;
     for (int f = threadIdx.x; f < Fp; f += blockDim.x) {
         const double v = (u < Nn) ? x[(int64_t)u * Fp + f] : 0.0;
         l1 += fabs(v);
-        long long ql = llrint(v * 16777216.0);
-        if (ql > 134000000LL || ql < -134000000LL) { atomicOr(flags, 1); ql = ql > 0 ? 134000000LL : -134000000LL; }
+        long long ql = llrint(v * inv_lattice);
+        if (ql > qcap || ql < -qcap) { atomicOr(flags, xl == 3 ? 2 : 1); ql = ql > 0 ? qcap : -qcap; }
         int q = (int)ql;
-        const int d3 = balanced_digit(q), d2 = balanced_digit(q), d1 = balanced_digit(q), d0 = q;
-        const int64_t row = ((int64_t)tile * X_LIMBS) * NODE_TILE1 + i;
-        X4[(row + 0 * NODE_TILE1) * Fp + f] = (int8_t)d0;
-        X4[(row + 1 * NODE_TILE1) * Fp + f] = (int8_t)d1;
-        X4[(row + 2 * NODE_TILE1) * Fp + f] = (int8_t)d2;
-        X4[(row + 3 * NODE_TILE1) * Fp + f] = (int8_t)d3;
+        int d[X_LIMBS_MAX];
+        for (int j = xl - 1; j > 0; --j) d[j] = balanced_digit(q);
+        d[0] = q;
+        const int64_t row = ((int64_t)tile * xl) * NODE_TILE1 + i;
+        for (int j = 0; j < xl; ++j) X[(row + (int64_t)j * NODE_TILE1) * Fp + f] = (int8_t)d[j];
     }
     for (int o = 16; o; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l1;
@@ -176,6 +181,7 @@ struct EnergyParams {
     int64_t block_stride;                  // pass b uses histogram block b * block_stride (strided subsample)
     int64_t r_rows_per_limb;               // Nn_pad2
     int nR, form, debug_skip_math;
+    float lattice;                         // value of one unit of the combined integer energy
     const float* w32;
     const float* inv_dr;                   // [Nn_pad1] 1/deltaR
     double* fsum;                          // [Nn_pad1] objective sums
@@ -207,9 +213,9 @@ __device__ __forceinline__ float fast_lg2(float x) {
 // so CTAs that run concurrently stream the SAME sample blocks for different node tiles (the P tiles are
 // shared through L2 instead of being re-read from HBM once per node tile), while each CTA keeps one node
 // tile for a whole sample range (objective partial sums stay in registers).
-template <int FORM, bool GRAD>
+template <int FORM, bool GRAD, int XL>
 __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_constant__ CUtensorMap tmA,   // P  [Kp x Fp]
-                                                                const __grid_constant__ CUtensorMap tmB,   // X4 [tiles*256 x Fp]
+                                                                const __grid_constant__ CUtensorMap tmB,   // X  [tiles*XL*64 x Fp], box XL*64 rows
                                                                 const __grid_constant__ CUtensorMap tmS,   // spins, sample-blocked [SB*Fspin x 128], box 64 rows
                                                                 const __grid_constant__ CUtensorMap tmR,   // R  [SB*nR*Nn_pad2 x 128], box 64 rows
                                                                 EnergyParams p) {
@@ -271,10 +277,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                     if (++slot == 2) { slot = 0; sphase ^= 1; }
                     for (int kb = 0; kb < kblocks; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], E_STAGE_BYTES);
+                        mbar_expect_tx(&full[stage], E_A_BYTES + XL * NODE_TILE1 * 128);
                         uint8_t* a = s_stage + stage * E_STAGE_BYTES;
                         tma_load_2d(a, &tmA, &full[stage], kb * 128, (int)(sb * 128));
-                        tma_load_2d(a + E_A_BYTES, &tmB, &full[stage], kb * 128, nt * 256);
+                        tma_load_2d(a + E_A_BYTES, &tmB, &full[stage], kb * 128, nt * XL * NODE_TILE1);
                         if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_i8(128, 256);
+            constexpr uint32_t idesc = make_idesc_i8(128, XL * NODE_TILE1);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -360,19 +366,21 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                     tmem_ld16(tbase + 0 * NODE_TILE1 + c * 16, a0);
                     tmem_ld16(tbase + 1 * NODE_TILE1 + c * 16, a1);
                     tmem_ld16(tbase + 2 * NODE_TILE1 + c * 16, a2);
-                    tmem_ld16(tbase + 3 * NODE_TILE1 + c * 16, a3);
+                    if (XL == 4) tmem_ld16(tbase + 3 * NODE_TILE1 + c * 16, a3);
                     tmem_ld_wait();
                     if (c == NPT / 16 - 1) {              // accumulator fully read: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty[as]);
                     }
-                    if (p.debug_skip_math) { facc[c] += (float)(a0[0] + a1[1] + a2[2] + a3[3]); continue; }
+                    if (p.debug_skip_math) { facc[c] += (float)(a0[0] + a1[1] + a2[2]); continue; }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int node_in_tile = half * NPT + c * 16 + i;
-                        const int hi = a0[i] * 128 + a1[i], lo = a2[i] * 128 + a3[i];
-                        const float e = fmaf((float)hi, 16384.f, (float)lo) * (float)X_LATTICE;
+                        // recombine the limb sums: exact integers, one rounding in the final fma
+                        const int hi = a0[i] * 128 + a1[i];
+                        const float e = (XL == 4 ? fmaf((float)hi, 16384.f, (float)(a2[i] * 128 + a3[i]))
+                                                 : fmaf((float)hi, 128.f, (float)a2[i])) * p.lattice;
                         const float su = (float)(int8_t)spin[node_in_tile * 128 + row];
                         const float t = su * e;
                         float fterm, gterm;
@@ -447,7 +455,7 @@ struct GradParams {
 
 constexpr int G_TILE_BYTES = 128 * 128;
 constexpr int64_t G_MAX_BLOCKS = 1 << 16;   // int32 accumulators: |acc| <= 64 * 128 * blocks < 2^31
-__host__ __device__ constexpr int g_stages(int nr) { return nr >= 4 ? 2 : 3; }
+__host__ __device__ constexpr int g_stages(int nr) { return nr >= 4 ? 2 : (nr == 3 ? 3 : 4); }
 
 // Work decomposition: item = (sample split ks, output tile), split-major and dealt round-robin, one item
 // per CTA when tiles * splits <= #SMs.  All CTAs of a split then sweep the SAME sample blocks in lockstep
@@ -624,9 +632,10 @@ CUtensorMap make_map_2d(const void* base, uint64_t inner, uint64_t outer, uint32
 
 struct BackendTC : EvalBackend {
     const NodeProblem& p;
-    int Nn_pad1, Nn_pad2, nR, n_sms;
+    int Nn_pad1, Nn_pad2, nR, n_sms;   // nR: residual limbs of the fine level
+    int level = 1;                      // 0 = coarse (3-limb iterate, nR-1 residual limbs), 1 = fine
     int32_t first_row = 0;   // spin rows of this shard are contiguous in `base`: spin_row[u] = first_row + u
-    DevBuf<int8_t> X4, R;
+    DevBuf<int8_t> X4, X3, R;
     DevBuf<float> inv_dr;
     DevBuf<double> delta;
     DevBuf<double> fsum;
@@ -637,7 +646,7 @@ struct BackendTC : EvalBackend {
     const int8_t* spin_blocked = nullptr;
     int Fspin = 0;
     DevBuf<int8_t> base_blocked;
-    CUtensorMap tmA, tmB, tmS, tmR, tmRa, tmQ;
+    CUtensorMap tmA, tmB, tmB3, tmS, tmR, tmRa, tmQ;
 
     BackendTC(const NodeProblem& prob, cudaStream_t st) : p(prob) {
         Histogram& h = *p.hist;
@@ -650,7 +659,8 @@ struct BackendTC : EvalBackend {
         GML_CUDA(cudaGetDevice(&dev));
         GML_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
         P = ensure_P(h, p.Q, p.Fp, st);
-        X4.alloc((size_t)Nn_pad1 * X_LIMBS * p.Fp);
+        X4.alloc((size_t)Nn_pad1 * 4 * p.Fp);
+        X3.alloc((size_t)Nn_pad1 * 3 * p.Fp);
         R.alloc((size_t)nR * Nn_pad2 * h.Kp);
         inv_dr.alloc(Nn_pad1); delta.alloc(Nn_pad1);
         fsum.alloc(Nn_pad1);
@@ -660,7 +670,8 @@ struct BackendTC : EvalBackend {
         // rows of R that belong to padding nodes are never written by GEMM-1 tiles beyond Nn_pad1: clear once
         GML_CUDA(cudaMemsetAsync(R.p, 0, (size_t)nR * Nn_pad2 * h.Kp, st));
         tmA = make_map_2d(P, p.Fp, h.Kp, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-        tmB = make_map_2d(X4.p, p.Fp, (uint64_t)Nn_pad1 * X_LIMBS, 128, 256, CU_TENSOR_MAP_SWIZZLE_128B);
+        tmB = make_map_2d(X4.p, p.Fp, (uint64_t)Nn_pad1 * 4, 128, 4 * NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_128B);
+        tmB3 = make_map_2d(X3.p, p.Fp, (uint64_t)Nn_pad1 * 3, 128, 3 * NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_128B);
         // Sample-blocked layouts: every TMA box is one contiguous 8/16 KB chunk (one 2 MB page) instead of
         // 64/128 rows that are Kp bytes apart.
         const uint64_t SB = (uint64_t)(h.Kp / 128);
@@ -688,16 +699,39 @@ struct BackendTC : EvalBackend {
         GML_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
     void configure() {
-        set_smem(tc_energy_kernel<GML_B200_RISE, true>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RISE, false>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RPLE, true>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RPLE, false>, E_SMEM);
+        set_smem(tc_energy_kernel<GML_B200_RISE, true, 4>, E_SMEM);
+        set_smem(tc_energy_kernel<GML_B200_RISE, false, 4>, E_SMEM);
+        set_smem(tc_energy_kernel<GML_B200_RPLE, true, 4>, E_SMEM);
+        set_smem(tc_energy_kernel<GML_B200_RPLE, false, 4>, E_SMEM);
+        set_smem(tc_energy_kernel<GML_B200_RISE, true, 3>, E_SMEM);
+        set_smem(tc_energy_kernel<GML_B200_RISE, false, 3>, E_SMEM);
+        set_smem(tc_energy_kernel<GML_B200_RPLE, true, 3>, E_SMEM);
+        set_smem(tc_energy_kernel<GML_B200_RPLE, false, 3>, E_SMEM);
+        set_smem(tc_grad_kernel<2>, grad_smem(2));
         set_smem(tc_grad_kernel<3>, grad_smem(3));
         set_smem(tc_grad_kernel<4>, grad_smem(4));
     }
     static int grad_smem(int nr) { return g_stages(nr) * (nr + 1) * G_TILE_BYTES + 1024 + 128; }
 
-    double lattice() const override { return X_LATTICE; }
+    double lattice() const override { return level == 0 ? X_LATTICE_COARSE : X_LATTICE_FINE; }
+    // rounding noise of a gradient component: ~0.29 sqrt(K) wmax e^B / qmax(nr); e^B ~ 20 as a typical upper value
+    double grad_noise() const override {
+        const Histogram& h = *p.hist;
+        const int nr = level == 0 ? std::max(2, nR - 1) : nR;
+        return std::max(1e-9, 0.29 * std::sqrt((double)h.K) * h.wmax * 20.0 / r_qmax(nr));
+    }
+    // level 0 needs |x| < 1 (checked by the quantiser: an overflow pins the backend to the fine level)
+    bool coarse_overflow = false;
+    bool set_level(int lv, cudaStream_t st) override {
+        if (lv == 0 && !coarse_overflow) {
+            int hf = 0;
+            GML_CUDA(cudaMemcpyAsync(&hf, flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            GML_CUDA(cudaStreamSynchronize(st));
+            coarse_overflow = (hf & 2) != 0;
+        }
+        level = (lv == 0 && !coarse_overflow) ? 0 : 1;
+        return level == lv;
+    }
 
     // ---- strided sample subsets (multilevel continuation): a pass uses every `stride`-th 128-sample block
     int64_t stride = 1;
@@ -734,12 +768,15 @@ struct BackendTC : EvalBackend {
 
     void eval(const double* x, bool want_grad, double* f_out, double* g_out, cudaStream_t st) override {
         const Histogram& h = *p.hist;
-        tc_quantize_x_kernel<<<Nn_pad1, 128, 0, st>>>(x, p.Nn, p.Fp, p.form, h.wmax, nR, X4.p, inv_dr.p, delta.p, flags.p);
+        const int xl = level == 0 ? 3 : 4;
+        const int nr = level == 0 ? std::max(2, nR - 1) : nR;      // residual limbs of this pass
+        tc_quantize_x_kernel<<<Nn_pad1, 128, 0, st>>>(x, p.Nn, p.Fp, p.form, h.wmax, nr, xl, 1.0 / lattice(), xl == 3 ? X3.p : X4.p,
+                                                      inv_dr.p, delta.p, flags.p);
         GML_LAUNCHED();
         GML_CUDA(cudaMemsetAsync(fsum.p, 0, sizeof(double) * Nn_pad1, st));
         EnergyParams ep{};
         ep.Kp = h.Kp; ep.Fp = p.Fp; ep.Fspin = Fspin; ep.Nn = p.Nn; ep.n_tiles = Nn_pad1 / NODE_TILE1;
-        ep.block_stride = stride; ep.sample_blocks = ceil_div(h.Kp / 128, stride); ep.r_rows_per_limb = Nn_pad2; ep.nR = nR; ep.form = p.form;
+        ep.block_stride = stride; ep.sample_blocks = ceil_div(h.Kp / 128, stride); ep.r_rows_per_limb = Nn_pad2; ep.nR = nr; ep.form = p.form; ep.lattice = (float)lattice();
         ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p;
         ep.debug_skip_math = std::getenv("GML_TC_DEBUG_SKIP_MATH") ? 1 : 0;
         ep.node_begin_row = first_row;
@@ -747,25 +784,28 @@ struct BackendTC : EvalBackend {
         const int grid1 = std::min(n_sms, ep.n_tiles * ep.n_groups);
         const bool rple = p.form == GML_B200_RPLE;
         span_begin(want_grad ? 0 : 2, st);
-        if (want_grad) {
-            if (rple) tc_energy_kernel<GML_B200_RPLE, true><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
-            else tc_energy_kernel<GML_B200_RISE, true><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
+#define GML_TC_ENERGY(FORM, GRAD, XL, MAPB) tc_energy_kernel<FORM, GRAD, XL><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, MAPB, tmS, tmR, ep)
+        if (xl == 4) {
+            if (want_grad) { if (rple) GML_TC_ENERGY(GML_B200_RPLE, true, 4, tmB); else GML_TC_ENERGY(GML_B200_RISE, true, 4, tmB); }
+            else { if (rple) GML_TC_ENERGY(GML_B200_RPLE, false, 4, tmB); else GML_TC_ENERGY(GML_B200_RISE, false, 4, tmB); }
         } else {
-            if (rple) tc_energy_kernel<GML_B200_RPLE, false><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
-            else tc_energy_kernel<GML_B200_RISE, false><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, tmB, tmS, tmR, ep);
+            if (want_grad) { if (rple) GML_TC_ENERGY(GML_B200_RPLE, true, 3, tmB3); else GML_TC_ENERGY(GML_B200_RISE, true, 3, tmB3); }
+            else { if (rple) GML_TC_ENERGY(GML_B200_RPLE, false, 3, tmB3); else GML_TC_ENERGY(GML_B200_RISE, false, 3, tmB3); }
         }
+#undef GML_TC_ENERGY
         GML_LAUNCHED();
         span_end(st);
         if (want_grad) {
             GML_CUDA(cudaMemsetAsync(G64.p, 0, sizeof(long long) * Nn_pad2 * p.Fp, st));
             GradParams gp{};
-            gp.Fp = p.Fp; gp.m_tiles = Nn_pad2 / 128; gp.f_tiles = p.Fp / 128; gp.nR = nR;
+            gp.Fp = p.Fp; gp.m_tiles = Nn_pad2 / 128; gp.f_tiles = p.Fp / 128; gp.nR = nr;
             gp.r_rows_per_limb = Nn_pad2; gp.block_stride = stride; gp.sample_blocks = ceil_div(h.Kp / 128, stride); gp.G = G64.p;
             const int tiles = gp.m_tiles * gp.f_tiles;
             gp.n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / tiles, gp.sample_blocks));
             const int grid2 = std::min(n_sms, tiles * gp.n_splits);
             span_begin(1, st);
-            if (nR == 3) tc_grad_kernel<3><<<grid2, 192, grad_smem(3), st>>>(tmRa, tmQ, gp);
+            if (nr == 2) tc_grad_kernel<2><<<grid2, 192, grad_smem(2), st>>>(tmRa, tmQ, gp);
+            else if (nr == 3) tc_grad_kernel<3><<<grid2, 192, grad_smem(3), st>>>(tmRa, tmQ, gp);
             else tc_grad_kernel<4><<<grid2, 192, grad_smem(4), st>>>(tmRa, tmQ, gp);
             GML_LAUNCHED();
             span_end(st);

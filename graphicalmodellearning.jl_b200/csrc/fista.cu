@@ -32,6 +32,8 @@ struct FistaState {
     int *stall, *streak;
     int* status;      // 0 active, 1 converged, 2 stalled at the gradient noise floor
     int* n_active;
+    unsigned long long* gmax;   // bits of the largest gradient-mapping norm over the active nodes of this round
+    int fine;                   // 1: the backend runs at its fine precision level
 };
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
         s.c[u] = 0.5 * L * q2;
         s.gmap[u] = L * dm;          // max-norm of the prox-gradient mapping at Y
         s.tn[u] = tn;
+        atomicMax(s.gmax, (unsigned long long)__double_as_longlong(L * dm));   // non-negative doubles order like their bits
     }
 }
 
@@ -108,8 +111,10 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
     const int64_t o = (int64_t)u * s.Fp;
     const double gm = s.gmap[u];
     // ---- convergence is decided at Y (whose gradient is known): the prox point Z is the answer
-    // (on a lattice backend a prox step of at most one lattice unit is the finest resolvable fixed point)
-    if (gm <= s.tol || (s.lattice > 0.0 && gm <= 1.01 * s.L[u] * s.lattice)) {
+    // (on a lattice backend a prox step of at most one lattice unit is the finest resolvable fixed point; nodes never
+    // retire on the coarse precision level, whose lattice and gradient noise are above the tolerance)
+    const bool conv = s.fine && (gm <= s.tol || (s.lattice > 0.0 && gm <= 1.01 * s.L[u] * s.lattice && gm <= 4.0 * s.tol));
+    if (conv) {
         for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) s.X[o + f] = s.Z[o + f];
         if (threadIdx.x == 0) s.status[u] = 1;
         return;
@@ -192,10 +197,11 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     const size_t nx = (size_t)Nn * Fp;
     DevBuf<double> Z, Y, Yn, G, Gn, fY, fYn, L, t, tn, q, c, gmap, best;
     DevBuf<int> status, n_active, stall, streak;
+    DevBuf<unsigned long long> gmax;
     r.x.alloc(nx); r.objective.alloc(Nn);
     Z.alloc(nx); Y.alloc(nx); Yn.alloc(nx); G.alloc(nx); Gn.alloc(nx);
     fY.alloc(Nn); fYn.alloc(Nn); L.alloc(Nn); t.alloc(Nn); tn.alloc(Nn); q.alloc(Nn); c.alloc(Nn); gmap.alloc(Nn);
-    status.alloc(Nn); n_active.alloc(1); best.alloc(Nn); stall.alloc(Nn); streak.alloc(Nn);
+    status.alloc(Nn); n_active.alloc(1); best.alloc(Nn); stall.alloc(Nn); streak.alloc(Nn); gmax.alloc(1);
     if (prob.x0) GML_CUDA(cudaMemcpyAsync(r.x.p, prob.x0, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
     else GML_CUDA(cudaMemsetAsync(r.x.p, 0, nx * sizeof(double), st));
     GML_CUDA(cudaMemsetAsync(Y.p, 0, nx * sizeof(double), st));
@@ -207,12 +213,11 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     s.lattice = be->lattice();
     s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
     s.eps_f = 1e-6;   // generous upper bound of the evaluation noise of f
-    s.eps_g = backend == GML_B200_SOLVER_FISTA_TC ? 1e-7 : 5e-6;   // absolute noise of a gradient component (per unit weight mass)
     s.best = best.p; s.stall = stall.p; s.streak = streak.p;
     s.pen = prob.pen.p;
     s.X = r.x.p; s.Z = Z.p; s.Y = Y.p; s.Yn = Yn.p; s.G = G.p; s.Gn = Gn.p;
     s.fY = fY.p; s.fYn = fYn.p; s.L = L.p; s.t = t.p; s.tn = tn.p; s.q = q.p; s.c = c.p; s.gmap = gmap.p;
-    s.obj = r.objective.p; s.status = status.p; s.n_active = n_active.p;
+    s.obj = r.objective.p; s.status = status.p; s.n_active = n_active.p; s.gmax = gmax.p; s.fine = 1;
 
     double t_setup = 0, t_loop = 0;
     if (o.verbose > 0) { GML_CUDA(cudaStreamSynchronize(st)); t_setup = tick(); }
@@ -242,23 +247,52 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
         const double scale = scale_free ? 1.0 : rho;
         // weights are not renormalised: f_level = rho * (normalised f), so lambda, L and the tolerance scale by rho
         s.lambda = prob.lambda * scale;
-        s.eps_g = (backend == GML_B200_SOLVER_FISTA_TC ? 1e-7 : 5e-6) * scale;
         s.tol = scale * (last ? user_tol : std::max(user_tol, 0.1 / std::sqrt(std::max(hist.M * rho, 1.0))));
         fista_init_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s, li == 0 ? scale : -(scale_free ? 1.0 : rho / rho_prev));
         GML_LAUNCHED();
         rho_prev = rho;
         GML_CUDA(cudaMemcpyAsync(Y.p, r.x.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));   // warm start
+        // Precision levels: while the gradient mapping is far above the coarse lattice the passes run with a
+        // 3-limb iterate (lattice 2^-20) and one residual limb less; the last rounds run at full precision.
+        // Coarse-lattice points are fine-lattice points, so the switch needs no re-evaluation.
+        const double coarse_exit = 2e-4 * scale;
+        int level = (o.reserved[3] == 0 && user_tol <= 1e-4 && be->set_level(0, st)) ? 0 : 1;
+        if (level == 1) be->set_level(1, st);
+        auto sync_level = [&] {
+            s.fine = level; s.lattice = be->lattice(); s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
+            s.eps_g = be->grad_noise() * scale;
+        };
+        sync_level();
         be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += 1.0 / stride;
         active = Nn;
         for (; it < max_iter; ++it) {
+            GML_CUDA(cudaMemsetAsync(gmax.p, 0, sizeof(unsigned long long), st));
             fista_trial_kernel<<<Nn, 128, 0, st>>>(s);
             GML_LAUNCHED();
             be->eval(Yn.p, true, fYn.p, Gn.p, st); ++n_fg; fg_units += 1.0 / stride;
             GML_CUDA(cudaMemsetAsync(n_active.p, 0, sizeof(int), st));
             fista_accept_kernel<<<Nn, 128, 0, st>>>(s);
             GML_LAUNCHED();
+            double h_gmax = 0.0;
             GML_CUDA(cudaMemcpyAsync(&active, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            GML_CUDA(cudaMemcpyAsync(&h_gmax, gmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
             GML_CUDA(cudaStreamSynchronize(st));
+            if (level == 0) {
+                const bool overflow = !be->set_level(0, st);       // some |x| reached 1: the 3-limb range is exhausted
+                if (overflow || h_gmax <= coarse_exit || active == 0) {
+                    level = 1; be->set_level(1, st); sync_level();
+                    if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista: fine precision from round %d (gmap max %.3g%s)\n", it + 1, h_gmax, overflow ? ", coarse range overflow" : "");
+                    if (overflow || active == 0) {
+                        // restart from the last accepted iterate at full precision
+                        fista_init_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s, -1.0);
+                        GML_LAUNCHED();
+                        GML_CUDA(cudaMemcpyAsync(Y.p, r.x.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                        active = Nn;
+                    }
+                    // the stored (f, G) at Y carry the coarse level's rounding noise: refresh them at full precision
+                    be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += 1.0 / stride;
+                }
+            }
             if (o.verbose > 1) {
                 std::vector<double> hg(Nn), hL(Nn);
                 GML_CUDA(cudaMemcpy(hg.data(), gmap.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost));

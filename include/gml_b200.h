@@ -57,7 +57,8 @@ typedef struct gml_b200_opts {
     void* stream;       /* cudaStream_t to launch on; NULL = the handle's own stream */
     int32_t reserved[8]; /* reserved[0] != 0: time the contraction kernels with CUDA events (stats.reserved_d);
                             reserved[1] != 0: enable the multilevel (sample-subset) continuation of the FISTA solvers;
-                            reserved[2] != 0: sample-sharded solve (see gml_b200_comm_init) */
+                            reserved[2] != 0: sample-sharded solve (see gml_b200_comm_init);
+                            reserved[3] != 0: disable the coarse precision level of the tensor-core FISTA solver */
 } gml_b200_opts;
 
 typedef struct gml_b200_stats {

@@ -89,7 +89,10 @@ def test_c2_kkt_recovery_symmetry(c2_session, form_cls, c):
 
 
 def test_c2_node_shards_equal_full_solve(c2_session):
-    """Node problems are independent: solving shards [0,37) and [37,100) gives the rows of the full solve."""
+    """Node problems are independent: solving shards [0,37) and [37,100) gives the rows of the full solve, up to the
+    solver tolerance (the round at which the passes switch from the coarse to the fine precision level is decided by
+    the slowest node of the solve, so shard and full solves follow slightly different paths to the same optimum).
+    With the coarse level disabled the rows agree to 1e-9."""
     import torch
     sess, _, _ = c2_session
     n = 100
@@ -100,7 +103,16 @@ def test_c2_node_shards_equal_full_solve(c2_session):
         sess.solve_pairwise_device(RISE(0.4, False), B200(), out.data_ptr(), b, e)
         torch.cuda.synchronize()
         rows.append(out.cpu().numpy())
-    assert np.abs(np.vstack(rows) - full).max() <= 1e-9
+    assert np.abs(np.vstack(rows) - full).max() <= 5e-6
+    exact = B200(coarse_level=False)
+    full2 = sess.solve_pairwise(RISE(0.4, False), exact)
+    rows2 = []
+    for b, e in ((0, 37), (37, 100)):
+        out = torch.empty((e - b, n), dtype=torch.float64, device="cuda")
+        sess.solve_pairwise_device(RISE(0.4, False), exact, out.data_ptr(), b, e)
+        torch.cuda.synchronize()
+        rows2.append(out.cpu().numpy())
+    assert np.abs(np.vstack(rows2) - full2).max() <= 1e-9
 
 
 def test_device_histogram_builder_and_sampler():
