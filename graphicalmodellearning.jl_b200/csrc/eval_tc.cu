@@ -196,7 +196,9 @@ constexpr int E_THREADS = 64 + 32 * E_EPI_WARPS;
 constexpr int E_A_BYTES = 128 * 128, E_B_BYTES = 256 * 128, E_STAGE_BYTES = E_A_BYTES + E_B_BYTES;
 constexpr int E_S_BYTES = NODE_TILE1 * 128;          // spins tile of the node block
 constexpr int E_R_BYTES_PER_LIMB = NODE_TILE1 * 128; // staging for the R limbs
-constexpr int E_SMEM = E_STAGES * E_STAGE_BYTES + 2 * E_S_BYTES + 4 * E_R_BYTES_PER_LIMB + 1024 /*align*/ + 512 /*barriers, scales*/;
+constexpr int E_R_BUF_BYTES = 4 * E_R_BYTES_PER_LIMB;   // one staging buffer (up to 4 limbs); two of them, used alternately
+constexpr int E_SMEM = E_STAGES * E_STAGE_BYTES + 2 * E_S_BYTES + 2 * E_R_BUF_BYTES + 1024 /*align*/ + 512 /*barriers, scales*/;
+static_assert(E_SMEM <= 227 * 1024, "energy kernel exceeds the shared memory of an SM");
 
 __device__ __forceinline__ float fast_ex2(float x) {
     float y;
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
     uint8_t* s_stage = smem;
     uint8_t* s_spin = smem + E_STAGES * E_STAGE_BYTES;
     uint8_t* s_r = s_spin + 2 * E_S_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + 4 * E_R_BYTES_PER_LIMB);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + 2 * E_R_BUF_BYTES);
     uint64_t* full = bars;                    // [E_STAGES]
     uint64_t* empty = bars + E_STAGES;        // [E_STAGES]
     uint64_t* tfull = bars + 2 * E_STAGES;    // [2]
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
         float facc[NPT];
         int as = 0; uint32_t aphase = 0;
         int slot = 0; uint32_t sphase = 0;
+        int rbuf = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int nt; int64_t b0, b1;
             item_range(item, nt, b0, b1);
@@ -354,10 +357,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                 mbar_wait(&sfull[slot], sphase);
                 mbar_wait(&tfull[as], aphase);
                 tc_fence_after();
-                if (GRAD) {
-                    if (et == 0) tma_store_wait_read();   // previous block's stores have drained the staging buffer
-                    named_bar_sync(1, EPI_THREADS);
-                }
+                // R staging is double buffered: block b writes buffer b&1 while the TMA store of block b-1 still
+                // reads the other one; the single barrier below also publishes that store b-1 has drained.
+                uint8_t* s_rb = s_r + (rbuf ? E_R_BUF_BYTES : 0);
                 const uint8_t* spin = s_spin + slot * E_S_BYTES;
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256 + half * NPT;
 #pragma unroll
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                         facc[c * 16 + i] += fterm;
                         if (GRAD) {
                             int q = __float2int_rn(su * gterm * s_scale[node_in_tile]);
-                            uint8_t* dst = s_r + node_in_tile * 128 + row;
+                            uint8_t* dst = s_rb + node_in_tile * 128 + row;
                             const int d_lo = balanced_digit(q);
                             if (p.nR == 2) {
                                 dst[0 * E_R_BYTES_PER_LIMB] = (uint8_t)q;
@@ -422,10 +424,12 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                 if (lane == 0) mbar_arrive(&sempty[slot]);
                 if (GRAD) {
                     fence_proxy_async();
+                    if (et == 0) tma_store_wait_read();   // store of block b-1 has finished reading the other buffer
                     named_bar_sync(1, EPI_THREADS);
+                    rbuf ^= 1;
                     if (et == 0) {
                         for (int j = 0; j < p.nR; ++j)
-                            tma_store_2d(&tmR, s_r + j * E_R_BYTES_PER_LIMB, 0,
+                            tma_store_2d(&tmR, s_rb + j * E_R_BYTES_PER_LIMB, 0,
                                          (int)((sb * p.nR + j) * p.r_rows_per_limb) + nt * NODE_TILE1);
                         tma_store_commit();
                     }

@@ -266,13 +266,26 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
         be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += 1.0 / stride;
         active = Nn;
         for (; it < max_iter; ++it) {
+            const bool trace = o.verbose > 2 && it == 5;     // one round dissected with events
+            cudaEvent_t ev[4];
+            if (trace) for (auto& e : ev) cudaEventCreate(&e);
+            if (trace) cudaEventRecord(ev[0], st);
             GML_CUDA(cudaMemsetAsync(gmax.p, 0, sizeof(unsigned long long), st));
             fista_trial_kernel<<<Nn, 128, 0, st>>>(s);
             GML_LAUNCHED();
+            if (trace) cudaEventRecord(ev[1], st);
             be->eval(Yn.p, true, fYn.p, Gn.p, st); ++n_fg; fg_units += 1.0 / stride;
+            if (trace) cudaEventRecord(ev[2], st);
             GML_CUDA(cudaMemsetAsync(n_active.p, 0, sizeof(int), st));
             fista_accept_kernel<<<Nn, 128, 0, st>>>(s);
             GML_LAUNCHED();
+            if (trace) {
+                cudaEventRecord(ev[3], st); cudaEventSynchronize(ev[3]);
+                float a, b, c;
+                cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
+                fprintf(stderr, "[gml_b200] round %d: trial %.3f ms, pass %.3f ms, accept %.3f ms\n", it, a, b, c);
+                for (auto& e : ev) cudaEventDestroy(e);
+            }
             double h_gmax = 0.0;
             GML_CUDA(cudaMemcpyAsync(&active, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             GML_CUDA(cudaMemcpyAsync(&h_gmax, gmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
