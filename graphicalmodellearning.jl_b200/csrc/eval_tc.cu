@@ -176,11 +176,12 @@ __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __rest
 struct EnergyParams {
     int64_t Kp;
     int Fp, Fspin, Nn, n_tiles, node_begin_row;   // node tile t covers spin rows node_begin_row + 64 t ... of each [Fspin x 128] block
+    int spin_vec;                          // 1: the spin tile comes from P, sample-major [128 samples][64 nodes] (16 B per thread)
     int n_groups;                          // sample ranges; work item = (group, node tile)
     int64_t sample_blocks;                 // sample blocks of this pass (Kp / 128 / block_stride)
     int64_t block_stride;                  // pass b uses histogram block b * block_stride (strided subsample)
     int64_t r_rows_per_limb;               // Nn_pad2
-    int nR, form, debug_skip_math;
+    int nR, form;
     float lattice;                         // value of one unit of the combined integer energy
     const float* w32;
     const float* inv_dr;                   // [Nn_pad1] 1/deltaR
@@ -200,6 +201,25 @@ constexpr int E_R_BUF_BYTES = 4 * E_R_BYTES_PER_LIMB;   // one staging buffer (u
 constexpr int E_SMEM = E_STAGES * E_STAGE_BYTES + 2 * E_S_BYTES + 2 * E_R_BUF_BYTES + 1024 /*align*/ + 512 /*barriers, scales*/;
 static_assert(E_SMEM <= 227 * 1024, "energy kernel exceeds the shared memory of an SM");
 
+// explicit shared-space accesses (the carved-up dynamic smem pointer is generic to the compiler, which would
+// otherwise emit generic LD/ST for every epilogue access)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 __device__ __forceinline__ float fast_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -215,10 +235,11 @@ __device__ __forceinline__ float fast_lg2(float x) {
 // so CTAs that run concurrently stream the SAME sample blocks for different node tiles (the P tiles are
 // shared through L2 instead of being re-read from HBM once per node tile), while each CTA keeps one node
 // tile for a whole sample range (objective partial sums stay in registers).
-template <int FORM, bool GRAD, int XL>
+template <int FORM, bool GRAD, int XL, int NR>
 __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_constant__ CUtensorMap tmA,   // P  [Kp x Fp]
                                                                 const __grid_constant__ CUtensorMap tmB,   // X  [tiles*XL*64 x Fp], box XL*64 rows
-                                                                const __grid_constant__ CUtensorMap tmS,   // spins, sample-blocked [SB*Fspin x 128], box 64 rows
+                                                                const __grid_constant__ CUtensorMap tmS,   // spins, sample-blocked [SB*Fspin x 128], box 64 rows (row coordinates need no alignment)
+                                                                const __grid_constant__ CUtensorMap tmSv,  // P, box {64 nodes, 128 samples}: used when the shard's first spin column is 16-byte aligned
                                                                 const __grid_constant__ CUtensorMap tmR,   // R  [SB*nR*Nn_pad2 x 128], box 64 rows
                                                                 EnergyParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -247,7 +268,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
             mbar_init(&sfull[i], 1); mbar_init(&sempty[i], E_EPI_WARPS);
         }
         fence_barrier_init();
-        prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmS);
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmS); prefetch_tmap(&tmSv);
         if (GRAD) prefetch_tmap(&tmR);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -275,7 +296,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                     const int64_t sb = eb * p.block_stride;
                     mbar_wait(&sempty[slot], sphase ^ 1);
                     mbar_expect_tx(&sfull[slot], E_S_BYTES);
-                    tma_load_2d(s_spin + slot * E_S_BYTES, &tmS, &sfull[slot], 0, (int)(sb * p.Fspin) + p.node_begin_row + nt * NODE_TILE1);
+                    if (p.spin_vec) tma_load_2d(s_spin + slot * E_S_BYTES, &tmSv, &sfull[slot], p.node_begin_row + nt * NODE_TILE1, (int)(sb * 128));
+                    else tma_load_2d(s_spin + slot * E_S_BYTES, &tmS, &sfull[slot], 0, (int)(sb * p.Fspin) + p.node_begin_row + nt * NODE_TILE1);
                     if (++slot == 2) { slot = 0; sphase ^= 1; }
                     for (int kb = 0; kb < kblocks; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
@@ -359,11 +381,29 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                 tc_fence_after();
                 // R staging is double buffered: block b writes buffer b&1 while the TMA store of block b-1 still
                 // reads the other one; the single barrier below also publishes that store b-1 has drained.
+                const uint32_t rb_addr = smem_u32(s_r) + (rbuf ? E_R_BUF_BYTES : 0) + row;
                 uint8_t* s_rb = s_r + (rbuf ? E_R_BUF_BYTES : 0);
-                const uint8_t* spin = s_spin + slot * E_S_BYTES;
+                // spins of this thread's nodes: either 16 contiguous bytes of the sample-major tile [128 samples][64 nodes]
+                // or one byte per node at column `row` of the node-major tile [64 nodes][128 samples]
+                const uint32_t spin_base = smem_u32(s_spin) + slot * E_S_BYTES;
+                const uint32_t spin_addr = p.spin_vec ? spin_base + row * NODE_TILE1 + half * NPT : spin_base + half * NPT * 128 + row;
+                const uint32_t scale_addr = smem_u32(s_scale) + 4 * half * NPT;
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256 + half * NPT;
+                const float c_arg = -p.lattice * 1.4426950408889634f;      // exp(-t) = ex2(c_arg * s_u * E_int)
+                constexpr int R_BIAS = NR == 2 ? 64 * 129 : (NR == 3 ? 64 * 16513 : 64 * 2113665);
 #pragma unroll
                 for (int c = 0; c < NPT / 16; ++c) {
+                    uint32_t sw[4];                       // the 16 spin bytes of this chunk, packed
+                    if (p.spin_vec) {
+                        const uint4 v = lds128(spin_addr + c * 16);
+                        sw[0] = v.x; sw[1] = v.y; sw[2] = v.z; sw[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const uint32_t b = spin_addr + (c * 16 + 4 * w) * 128;
+                            sw[w] = lds_u8(b) | (lds_u8(b + 128) << 8) | (lds_u8(b + 256) << 16) | (lds_u8(b + 384) << 24);
+                        }
+                    }
                     int32_t a0[16], a1[16], a2[16], a3[16];
                     tmem_ld16(tbase + 0 * NODE_TILE1 + c * 16, a0);
                     tmem_ld16(tbase + 1 * NODE_TILE1 + c * 16, a1);
@@ -375,48 +415,38 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty[as]);
                     }
-                    if (p.debug_skip_math) { facc[c] += (float)(a0[0] + a1[1] + a2[2]); continue; }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int node_in_tile = half * NPT + c * 16 + i;
-                        // recombine the limb sums: exact integers, one rounding in the final fma
-                        const int hi = a0[i] * 128 + a1[i];
-                        const float e = (XL == 4 ? fmaf((float)hi, 16384.f, (float)(a2[i] * 128 + a3[i]))
-                                                 : fmaf((float)hi, 128.f, (float)a2[i])) * p.lattice;
-                        const float su = (float)(int8_t)spin[node_in_tile * 128 + row];
-                        const float t = su * e;
+                        const int nit = c * 16 + i;                           // node within this thread's slice
+                        // sign bit of s_u (bytes are 0x01 / 0xFF; 0x00 for padding nodes)
+                        const uint32_t sgn = ((i & 3) == 3 ? sw[i >> 2] : (sw[i >> 2] << (24 - 8 * (i & 3)))) & 0x80000000u;
+                        // recombine the limb sums: exact integers, at most one rounding
+                        float e;
+                        if (XL == 3) e = __int2float_rn((a0[i] * 128 + a1[i]) * 128 + a2[i]);
+                        else e = fmaf(__int2float_rn(a0[i] * 128 + a1[i]), 16384.f, __int2float_rn(a2[i] * 128 + a3[i]));
+                        const float es = __uint_as_float(__float_as_uint(e) ^ sgn);        // s_u * E / lattice
                         float fterm, gterm;
                         if (FORM == GML_B200_RPLE) {
-                            const float a = -2.f * t;
+                            const float a = -2.f * p.lattice * es;
                             const float ex = fast_ex2(-fabsf(a) * 1.4426950408889634f);
                             fterm = wk * fmaf(fast_lg2(1.f + ex), 0.6931471805599453f, fmaxf(a, 0.f));
                             gterm = __fdividef(2.f * wk * (a > 0.f ? 1.f : ex), 1.f + ex);   // 2 w sigma(-2t)
                         } else {
-                            fterm = wk * fast_ex2(fminf(-t, 80.f) * 1.4426950408889634f);
+                            fterm = wk * fast_ex2(fminf(es * c_arg, 115.f));
                             gterm = fterm;
                         }
-                        facc[c * 16 + i] += fterm;
+                        facc[nit] += fterm;
                         if (GRAD) {
-                            int q = __float2int_rn(su * gterm * s_scale[node_in_tile]);
-                            uint8_t* dst = s_rb + node_in_tile * 128 + row;
-                            const int d_lo = balanced_digit(q);
-                            if (p.nR == 2) {
-                                dst[0 * E_R_BYTES_PER_LIMB] = (uint8_t)q;
-                                dst[1 * E_R_BYTES_PER_LIMB] = (uint8_t)d_lo;
-                            } else {
-                                const int d_mid = balanced_digit(q);
-                                if (p.nR == 3) {
-                                    dst[0 * E_R_BYTES_PER_LIMB] = (uint8_t)q;
-                                    dst[1 * E_R_BYTES_PER_LIMB] = (uint8_t)d_mid;
-                                    dst[2 * E_R_BYTES_PER_LIMB] = (uint8_t)d_lo;
-                                } else {
-                                    const int d_2 = balanced_digit(q);
-                                    dst[0 * E_R_BYTES_PER_LIMB] = (uint8_t)q;
-                                    dst[1 * E_R_BYTES_PER_LIMB] = (uint8_t)d_2;
-                                    dst[2 * E_R_BYTES_PER_LIMB] = (uint8_t)d_mid;
-                                    dst[3 * E_R_BYTES_PER_LIMB] = (uint8_t)d_lo;
-                                }
-                            }
+                            // r = s_u * gterm in units of the node's residual grid, rounded to nearest, plus the
+                            // bias that makes all balanced digits non-negative
+                            const float vq = __uint_as_float(__float_as_uint(gterm * lds_f32(scale_addr + 4 * nit)) ^ sgn);
+                            int qb;
+                            if (NR == 4) qb = __float2int_rn(vq) + R_BIAS;
+                            else qb = __float_as_int(vq + 12582912.f) - 0x4B400000 + R_BIAS;      // |vq| < 2^22
+                            const uint32_t dst = rb_addr + (half * NPT + nit) * 128;
+#pragma unroll
+                            for (int j = 0; j < NR; ++j)      // limb 0 = most significant digit
+                                sts_u8(dst + j * E_R_BYTES_PER_LIMB, ((qb >> (7 * (NR - 1 - j))) & 127) - 64);
                         }
                     }
                 }
@@ -428,9 +458,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                     named_bar_sync(1, EPI_THREADS);
                     rbuf ^= 1;
                     if (et == 0) {
-                        for (int j = 0; j < p.nR; ++j)
+                        for (int j = 0; j < NR; ++j)
                             tma_store_2d(&tmR, s_rb + j * E_R_BYTES_PER_LIMB, 0,
-                                         (int)((sb * p.nR + j) * p.r_rows_per_limb) + nt * NODE_TILE1);
+                                         (int)((sb * NR + j) * p.r_rows_per_limb) + nt * NODE_TILE1);
                         tma_store_commit();
                     }
                 }
@@ -650,7 +680,8 @@ struct BackendTC : EvalBackend {
     const int8_t* spin_blocked = nullptr;
     int Fspin = 0;
     DevBuf<int8_t> base_blocked;
-    CUtensorMap tmA, tmB, tmB3, tmS, tmR, tmRa, tmQ;
+    CUtensorMap tmA, tmB, tmB3, tmS, tmSv, tmR, tmRa, tmQ;
+    bool spin_vec = false;
 
     BackendTC(const NodeProblem& prob, cudaStream_t st) : p(prob) {
         Histogram& h = *p.hist;
@@ -679,7 +710,7 @@ struct BackendTC : EvalBackend {
         // Sample-blocked layouts: every TMA box is one contiguous 8/16 KB chunk (one 2 MB page) instead of
         // 64/128 rows that are Kp bytes apart.
         const uint64_t SB = (uint64_t)(h.Kp / 128);
-        GML_REQUIRE(SB * nR * Nn_pad2 < (1ull << 31) && SB * h.Fb < (1ull << 31) && SB * p.Fp < (1ull << 31),
+        GML_REQUIRE(SB * nR * Nn_pad2 < (1ull << 31) && SB * p.Fp < (1ull << 31),
                     "problem too large for 32-bit TMA row coordinates: shard the nodes or the samples");
         Qb = ensure_Qb(h, p.Q, p.Fp, st);
         // spins of the shard's nodes: for pairwise problems they are rows of Q itself; multibody problems
@@ -690,12 +721,16 @@ struct BackendTC : EvalBackend {
             launch_block_copy(h.base.p, base_blocked.p, h.Fb, h.Kp, st);
             spin_blocked = base_blocked.p; Fspin = h.Fb;
         }
+        GML_REQUIRE(SB * Fspin < (1ull << 31), "problem too large for 32-bit TMA row coordinates: shard the samples");
         tmS = make_map_2d(spin_blocked, 128, SB * Fspin, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
+        tmSv = make_map_2d(P, p.Fp, h.Kp, NODE_TILE1, 128, CU_TENSOR_MAP_SWIZZLE_NONE);
         tmR = make_map_2d(R.p, 128, SB * nR * Nn_pad2, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
         tmRa = make_map_2d(R.p, 128, SB * nR * Nn_pad2, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         tmQ = make_map_2d(Qb, 128, SB * p.Fp, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         GML_CUDA(cudaMemcpyAsync(&first_row, p.spin_row.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         GML_CUDA(cudaStreamSynchronize(st));
+        // vector spin loads need the shard's first spin column 16-byte aligned in P (TMA inner-dimension alignment)
+        spin_vec = (p.Q == h.base.p) && (first_row % 16 == 0);
         configure();
     }
 
@@ -703,14 +738,14 @@ struct BackendTC : EvalBackend {
         GML_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
     void configure() {
-        set_smem(tc_energy_kernel<GML_B200_RISE, true, 4>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RISE, false, 4>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RPLE, true, 4>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RPLE, false, 4>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RISE, true, 3>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RISE, false, 3>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RPLE, true, 3>, E_SMEM);
-        set_smem(tc_energy_kernel<GML_B200_RPLE, false, 3>, E_SMEM);
+#define GML_TC_SET(FORM, XL)                                               \
+        set_smem(tc_energy_kernel<FORM, false, XL, 2>, E_SMEM);                \
+        set_smem(tc_energy_kernel<FORM, true, XL, 2>, E_SMEM);                 \
+        set_smem(tc_energy_kernel<FORM, true, XL, 3>, E_SMEM);                 \
+        set_smem(tc_energy_kernel<FORM, true, XL, 4>, E_SMEM)
+        GML_TC_SET(GML_B200_RISE, 3); GML_TC_SET(GML_B200_RISE, 4);
+        GML_TC_SET(GML_B200_RPLE, 3); GML_TC_SET(GML_B200_RPLE, 4);
+#undef GML_TC_SET
         set_smem(tc_grad_kernel<2>, grad_smem(2));
         set_smem(tc_grad_kernel<3>, grad_smem(3));
         set_smem(tc_grad_kernel<4>, grad_smem(4));
@@ -782,20 +817,23 @@ struct BackendTC : EvalBackend {
         ep.Kp = h.Kp; ep.Fp = p.Fp; ep.Fspin = Fspin; ep.Nn = p.Nn; ep.n_tiles = Nn_pad1 / NODE_TILE1;
         ep.block_stride = stride; ep.sample_blocks = ceil_div(h.Kp / 128, stride); ep.r_rows_per_limb = Nn_pad2; ep.nR = nr; ep.form = p.form; ep.lattice = (float)lattice();
         ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p;
-        ep.debug_skip_math = std::getenv("GML_TC_DEBUG_SKIP_MATH") ? 1 : 0;
-        ep.node_begin_row = first_row;
+        ep.node_begin_row = first_row; ep.spin_vec = spin_vec ? 1 : 0;
         ep.n_groups = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / ep.n_tiles, ep.sample_blocks));
         const int grid1 = std::min(n_sms, ep.n_tiles * ep.n_groups);
         const bool rple = p.form == GML_B200_RPLE;
         span_begin(want_grad ? 0 : 2, st);
-#define GML_TC_ENERGY(FORM, GRAD, XL, MAPB) tc_energy_kernel<FORM, GRAD, XL><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, MAPB, tmS, tmR, ep)
-        if (xl == 4) {
-            if (want_grad) { if (rple) GML_TC_ENERGY(GML_B200_RPLE, true, 4, tmB); else GML_TC_ENERGY(GML_B200_RISE, true, 4, tmB); }
-            else { if (rple) GML_TC_ENERGY(GML_B200_RPLE, false, 4, tmB); else GML_TC_ENERGY(GML_B200_RISE, false, 4, tmB); }
-        } else {
-            if (want_grad) { if (rple) GML_TC_ENERGY(GML_B200_RPLE, true, 3, tmB3); else GML_TC_ENERGY(GML_B200_RISE, true, 3, tmB3); }
-            else { if (rple) GML_TC_ENERGY(GML_B200_RPLE, false, 3, tmB3); else GML_TC_ENERGY(GML_B200_RISE, false, 3, tmB3); }
-        }
+#define GML_TC_ENERGY(FORM, GRAD, XL, NRL, MAPB) \
+        tc_energy_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, MAPB, tmS, tmSv, tmR, ep)
+#define GML_TC_BY_NR(FORM, XL, MAPB)                                                        \
+        do {                                                                                \
+            if (!want_grad) GML_TC_ENERGY(FORM, false, XL, 2, MAPB);                        \
+            else if (nr == 2) GML_TC_ENERGY(FORM, true, XL, 2, MAPB);                       \
+            else if (nr == 3) GML_TC_ENERGY(FORM, true, XL, 3, MAPB);                       \
+            else GML_TC_ENERGY(FORM, true, XL, 4, MAPB);                                    \
+        } while (0)
+        if (xl == 4) { if (rple) GML_TC_BY_NR(GML_B200_RPLE, 4, tmB); else GML_TC_BY_NR(GML_B200_RISE, 4, tmB); }
+        else { if (rple) GML_TC_BY_NR(GML_B200_RPLE, 3, tmB3); else GML_TC_BY_NR(GML_B200_RISE, 3, tmB3); }
+#undef GML_TC_BY_NR
 #undef GML_TC_ENERGY
         GML_LAUNCHED();
         span_end(st);
