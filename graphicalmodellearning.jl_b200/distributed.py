@@ -29,14 +29,14 @@ def gather_rows(local_rows: torch.Tensor, n_nodes: int, group=None) -> torch.Ten
     if world == 1:
         return local_rows
     n_cols = local_rows.shape[1]
-    max_rows = -(-n_nodes // world)
+    cuts = [shard_bounds(n_nodes, world, r) for r in range(world)]
+    max_rows = max(e - b for b, e in cuts)
     padded = torch.zeros((max_rows, n_cols), dtype=local_rows.dtype, device=local_rows.device)
     padded[: local_rows.shape[0]] = local_rows
     out = torch.empty((world * max_rows, n_cols), dtype=local_rows.dtype, device=local_rows.device)
     dist.all_gather_into_tensor(out, padded, group=group)
     blocks = []
-    for r in range(world):
-        b, e = shard_bounds(n_nodes, world, r)
+    for r, (b, e) in enumerate(cuts):
         blocks.append(out[r * max_rows: r * max_rows + (e - b)])
     return torch.cat(blocks, dim=0)
 

@@ -47,6 +47,16 @@ def test_shard_bounds_cover_all_nodes():
                 assert max(sizes) - min(sizes) <= 1
 
 
+def test_gather_rows_handles_aligned_uneven_shards():
+    """N=1000 over 8 ranks: 16-aligned cuts give 7 x 128 + 104 rows; the gather must pad to the LARGEST shard."""
+    sys.path.insert(0, str(ROOT))
+    import gml_b200  # noqa: F401
+    from gml_b200.distributed import shard_bounds
+    cuts = [shard_bounds(1000, 8, r) for r in range(8)]
+    sizes = [e - b for b, e in cuts]
+    assert sum(sizes) == 1000 and max(sizes) == 128 and all(b % 16 == 0 for b, _ in cuts)
+
+
 def test_two_rank_gather_matches_oracle():
     for p in (ROOT, ROOT / "oracle", ROOT / "tests"):
         sys.path.insert(0, str(p))
