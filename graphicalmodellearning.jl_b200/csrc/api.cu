@@ -15,6 +15,18 @@ thread_local std::string g_error;
 thread_local int64_t g_launches = 0;
 void set_error(const std::string& msg) { g_error = msg; }
 
+void pool_init() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+}
+
 namespace {
 
 double now_ms() {

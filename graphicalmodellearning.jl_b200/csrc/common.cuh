@@ -38,16 +38,23 @@ extern thread_local int64_t g_launches;   // kernels launched by the current cal
 #define GML_LAUNCHED()                                                                         \
     do { ++::gml::g_launches; GML_CUDA(cudaGetLastError()); } while (0)
 
+// Device buffers come from the device's stream-ordered memory pool (retention threshold raised once per device
+// by pool_init): after the first solve the multi-GB work buffers of a solve are re-used instead of being mapped
+// and unmapped by cudaMalloc / cudaFree on every call.  Frees are issued only after the solve stream has been
+// synchronised (all entry points synchronise before their buffers go out of scope).
+void pool_init();
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     void alloc(size_t count) {
         if (count <= n && p) return;
         release();
-        GML_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        pool_init();
+        GML_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), cudaStreamLegacy));
+        GML_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
         n = count;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFreeAsync(p, cudaStreamLegacy); p = nullptr; n = 0; }
     ~DevBuf() { release(); }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
@@ -149,6 +156,10 @@ struct EvalBackend {
     // precision level of the following passes: 0 = coarse (cheaper, coarser lattice), 1 = fine.  Returns
     // whether the requested level was taken (backends without levels always run fine).
     virtual bool set_level(int lv, cudaStream_t) { return lv == 1; }
+    // device word whose bit 1 is raised when the coarse level's range overflowed (nullptr: no such condition);
+    // the driver reads it together with its own per-round counters to keep ONE host sync per round
+    virtual const int* device_flags() const { return nullptr; }
+    virtual void note_coarse_overflow() {}
     // estimated absolute noise of one gradient component at the current precision level (per unit weight mass)
     virtual double grad_noise() const { return 5e-6; }
     // optional per-kernel device timing (opts.reserved[0] != 0): out[0] = energy-kernel ms (full passes),

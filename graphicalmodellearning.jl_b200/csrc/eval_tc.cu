@@ -761,16 +761,12 @@ struct BackendTC : EvalBackend {
     }
     // level 0 needs |x| < 1 (checked by the quantiser: an overflow pins the backend to the fine level)
     bool coarse_overflow = false;
-    bool set_level(int lv, cudaStream_t st) override {
-        if (lv == 0 && !coarse_overflow) {
-            int hf = 0;
-            GML_CUDA(cudaMemcpyAsync(&hf, flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            GML_CUDA(cudaStreamSynchronize(st));
-            coarse_overflow = (hf & 2) != 0;
-        }
+    bool set_level(int lv, cudaStream_t) override {
         level = (lv == 0 && !coarse_overflow) ? 0 : 1;
         return level == lv;
     }
+    const int* device_flags() const override { return flags.p; }
+    void note_coarse_overflow() override { coarse_overflow = true; }
 
     // ---- strided sample subsets (multilevel continuation): a pass uses every `stride`-th 128-sample block
     int64_t stride = 1;

@@ -287,11 +287,15 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
                 for (auto& e : ev) cudaEventDestroy(e);
             }
             double h_gmax = 0.0;
+            int h_flags = 0;
             GML_CUDA(cudaMemcpyAsync(&active, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             GML_CUDA(cudaMemcpyAsync(&h_gmax, gmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-            GML_CUDA(cudaStreamSynchronize(st));
+            if (level == 0 && be->device_flags())
+                GML_CUDA(cudaMemcpyAsync(&h_flags, be->device_flags(), sizeof(int), cudaMemcpyDeviceToHost, st));
+            GML_CUDA(cudaStreamSynchronize(st));       // the only host sync of the round
             if (level == 0) {
-                const bool overflow = !be->set_level(0, st);       // some |x| reached 1: the 3-limb range is exhausted
+                const bool overflow = (h_flags & 2) != 0;           // some |x| reached 1: the 3-limb range is exhausted
+                if (overflow) be->note_coarse_overflow();
                 if (overflow || h_gmax <= coarse_exit || active == 0) {
                     level = 1; be->set_level(1, st); sync_level();
                     if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista: fine precision from round %d (gmap max %.3g%s)\n", it + 1, h_gmax, overflow ? ", coarse range overflow" : "");
