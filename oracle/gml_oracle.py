@@ -1,8 +1,9 @@
 """CPU oracle for the `learn()` hot path of lanl-ansi/GraphicalModelLearning.jl (v0.2.2).
 
 TEST INFRASTRUCTURE ONLY.  Nothing under `graphicalmodellearning.jl_b200/` may import this
-module; only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
-reference` legs use it, and only as the checker or as the timed CPU baseline.
+module; only `tests/` (including the developer checks under `tests/tools/`), `__graft_entry__.smoke()`
+and `bench.py`'s cpu_baseline / `--impl reference` legs use it, and only as the checker or as the timed
+CPU baseline.
 
 What it restates (float64 numpy; every function cites the reference lines it follows, all
 relative to /root/reference/):

@@ -1,6 +1,6 @@
 """Developer check (GPU box): error / iteration table of every solver x formulation on C1-sized input."""
 import sys, time, pathlib
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 for p in (ROOT, ROOT / "oracle", ROOT / "tests"):
     sys.path.insert(0, str(p))
 import numpy as np

@@ -1,6 +1,6 @@
 """Developer check (GPU box): f / gradient of the cc and tc backends against the float64 oracle."""
 import sys, pathlib
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 for p in (ROOT, ROOT / "oracle", ROOT / "tests"):
     sys.path.insert(0, str(p))
 import numpy as np

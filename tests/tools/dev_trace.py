@@ -1,6 +1,6 @@
 """Developer trace (GPU box): per-round FISTA diagnostics for one formulation on a C1-sized input."""
 import sys, pathlib
-ROOT = pathlib.Path(__file__).resolve().parent.parent
+ROOT = pathlib.Path(__file__).resolve().parent.parent.parent
 for p in (ROOT, ROOT / "oracle", ROOT / "tests"):
     sys.path.insert(0, str(p))
 import gml_b200
