@@ -161,8 +161,10 @@ def run_reference(args):
     value = last["value"] * last["seconds"] / np.mean(times)
     line = {"impl": "reference", "metric": "node_sample_evals_per_s", "value": value, "unit": "node*sample evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3 RISE N={n} 4-regular +-0.4 Ising, M={args.nsamples:g} (bounded sample: see cpu_baseline.sample)"},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3: learn() RISE(0.4,true), N={n} random 4-regular Ising J=+-0.4, M=K={int(args.nsamples):g} Gibbs samples "
+                                   f"({args.sweeps} sweeps/chain) -- CPU arm: bounded sample of this workload, see cpu_baseline.sample",
+                       "arithmetic": "float64 per-node prox-Newton (f, gradient, dense Hessian per iteration), OpenMP over nodes"},
             "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": value, "unit": "node*sample evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
