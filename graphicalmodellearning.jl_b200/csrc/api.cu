@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <thread>
 
 namespace gml {
 
@@ -612,9 +613,86 @@ int gml_b200_symmetrize_device(double* d_theta, int32_t N, void* stream) {
     });
 }
 
+// Single-process multi-GPU form of the one-shot call (opts->reserved[4] = number of devices): one host thread per
+// device, each with its own handle, the histogram replicated, node shards with 16-aligned cuts; every thread writes
+// its rows straight into the caller's matrix, the symmetrisation of the N x N result runs on the host.  This is what a
+// single Julia process uses; multi-process launches (torchrun) use gml_b200_solve_pairwise_device + an all-gather.
+static int learn_pairwise_multi_device(const double* counts, const int8_t* spins, int64_t K, int32_t N, int64_t ld,
+                                       int32_t formulation, double lambda, int32_t symmetrize, const gml_b200_opts& base,
+                                       int n_dev, double* out_theta, double* out_objective, gml_b200_stats* stats) {
+    const double t0 = now_ms();
+    std::vector<int> rcs(n_dev, GML_B200_OK);
+    std::vector<std::string> errs(n_dev);
+    std::vector<gml_b200_stats> sts(n_dev);
+    std::vector<std::thread> threads;
+    auto cut = [&](int r) {            // same rule as distributed.shard_bounds
+        const int per = N / n_dev, extra = N % n_dev;
+        int b = r * per + std::min(r, extra), e = b + per + (r < extra ? 1 : 0);
+        if (per >= 64) {
+            auto up = [&](int v) { return std::min(N, (v + 15) / 16 * 16); };
+            b = r == 0 ? 0 : up(b); e = r == n_dev - 1 ? N : up(e);
+        }
+        return std::make_pair(b, e);
+    };
+    for (int r = 0; r < n_dev; ++r)
+        threads.emplace_back([&, r] {
+            gml_b200_handle* h = nullptr;
+            gml_b200_opts o = base;
+            o.device = base.device + r;
+            const auto be = cut(r);
+            o.node_begin = be.first; o.node_end = be.second; o.stream = nullptr;
+            int rc = gml_b200_create(&h, o.device);
+            gml_b200_stats up{};
+            std::memset(&sts[r], 0, sizeof(gml_b200_stats));
+            if (rc == GML_B200_OK && be.first < be.second) {
+                rc = gml_b200_upload_histogram(h, counts, spins, K, N, ld, &up);
+                if (rc == GML_B200_OK)
+                    rc = gml_b200_solve_pairwise(h, formulation, lambda, 0, &o, out_theta, out_objective, &sts[r]);
+                sts[r].pack_ms = up.pack_ms; sts[r].h2d_ms = up.h2d_ms; sts[r].kernel_launches += up.kernel_launches;
+            }
+            if (rc != GML_B200_OK) errs[r] = gml_b200_last_error();
+            rcs[r] = rc;
+            gml_b200_destroy(h);
+        });
+    for (auto& t : threads) t.join();
+    int rc = GML_B200_OK;
+    for (int r = 0; r < n_dev; ++r)
+        if (rcs[r] != GML_B200_OK && (rc == GML_B200_OK || rc == GML_B200_ENOTCONV)) { rc = rcs[r]; set_error("device " + std::to_string(base.device + r) + ": " + errs[r]); }
+    if (symmetrize && (rc == GML_B200_OK || rc == GML_B200_ENOTCONV))
+        for (int i = 0; i < N; ++i)
+            for (int j = i + 1; j < N; ++j) {
+                const double v = 0.5 * (out_theta[(size_t)i + (size_t)N * j] + out_theta[(size_t)j + (size_t)N * i]);   // (:185)
+                out_theta[(size_t)i + (size_t)N * j] = v; out_theta[(size_t)j + (size_t)N * i] = v;
+            }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        for (int r = 0; r < n_dev; ++r) {
+            stats->solver_used = sts[r].solver_used;
+            stats->iterations = std::max(stats->iterations, sts[r].iterations);
+            stats->n_fg_passes = std::max(stats->n_fg_passes, sts[r].n_fg_passes);
+            stats->n_f_passes = std::max(stats->n_f_passes, sts[r].n_f_passes);
+            stats->n_unconverged += sts[r].n_unconverged;
+            stats->kernel_launches += sts[r].kernel_launches;
+            stats->evals += sts[r].evals;
+            stats->solve_ms = std::max(stats->solve_ms, sts[r].solve_ms);
+            stats->h2d_ms = std::max(stats->h2d_ms, sts[r].h2d_ms);
+            stats->pack_ms = std::max(stats->pack_ms, sts[r].pack_ms);
+            stats->max_residual = std::max(stats->max_residual, sts[r].max_residual);
+        }
+        stats->total_ms = now_ms() - t0;
+    }
+    return rc;
+}
+
 int gml_b200_learn_pairwise(const double* counts, const int8_t* spins, int64_t K, int32_t N, int64_t ld,
                             int32_t formulation, double lambda, int32_t symmetrize, const gml_b200_opts* opts,
                             double* out_theta, double* out_objective, gml_b200_stats* stats) {
+    if (opts && opts->reserved[4] > 1) {
+        const int n_dev = std::min<int>(opts->reserved[4], std::max(1, gml_b200_device_count() - opts->device));
+        if (n_dev > 1 && N >= 2 * n_dev)
+            return learn_pairwise_multi_device(counts, spins, K, N, ld, formulation, lambda, symmetrize, *opts, n_dev,
+                                               out_theta, out_objective, stats);
+    }
     gml_b200_handle* h = nullptr;
     int rc = gml_b200_create(&h, opts ? opts->device : 0);
     if (rc != GML_B200_OK) return rc;

@@ -106,19 +106,20 @@ void comm_allreduce_max_f64(Comm* c, double* buf, size_t n, cudaStream_t st) {
 void comm_globalize_histogram(Comm* c, Histogram& h, cudaStream_t st) {
     if (!c || c->world == 1) return;
     DevBuf<double> s;
-    s.alloc(2);
-    const double local[2] = {h.M, h.wmax * h.M};   // sum of counts, max count
+    s.alloc(3);
+    const double local[3] = {h.M, (double)h.K, h.wmax * h.M};   // sum of counts, rows, max count
     GML_CUDA(cudaMemcpyAsync(s.p, local, sizeof(local), cudaMemcpyHostToDevice, st));
-    comm_allreduce_sum_f64(c, s.p, 1, st);
-    comm_allreduce_max_f64(c, s.p + 1, 1, st);
-    double glob[2];
+    comm_allreduce_sum_f64(c, s.p, 2, st);
+    comm_allreduce_max_f64(c, s.p + 2, 1, st);
+    double glob[3];
     GML_CUDA(cudaMemcpyAsync(glob, s.p, sizeof(glob), cudaMemcpyDeviceToHost, st));
     GML_CUDA(cudaStreamSynchronize(st));
     rescale_weights_kernel<<<(unsigned)ceil_div(h.Kp, 256), 256, 0, st>>>(h.w64.p, h.w32.p, h.Kp, h.M / glob[0]);
     GML_LAUNCHED();
     h.M_local = h.M;
     h.M = glob[0];
-    h.wmax = glob[1] / glob[0];
+    h.K_total = glob[1];
+    h.wmax = glob[2] / glob[0];
 }
 
 }  // namespace gml

@@ -86,6 +86,7 @@ struct Histogram {
     int32_t Fb = 0;          // padded rows of `base`
     double M = 0.0;          // sum of counts (num_samples of data_info); global after comm_globalize_histogram
     double M_local = 0.0;    // this rank's share in sample-sharded mode (0 = not sharded)
+    double K_total = 0.0;    // histogram rows over all ranks (= K unless sample-sharded)
     double wmax = 0.0;       // max_k c_k / M
     DevBuf<int8_t> base;
     DevBuf<double> w64;      // [Kp] c_k / M

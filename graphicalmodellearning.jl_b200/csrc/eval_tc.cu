@@ -689,7 +689,7 @@ struct BackendTC : EvalBackend {
         Nn_pad2 = (int)round_up(p.Nn, NODE_TILE2);
         // Residual limbs: the rounding noise of the gradient is ~0.3 sqrt(K) wmax e^B / qmax(nR).  3 limbs
         // (qmax 1e6) keep it below 1e-8 for near-uniform counts; strongly weighted histograms get 4.
-        nR = (std::sqrt((double)h.K) * h.wmax > 2e-3) ? 4 : 3;
+        nR = (std::sqrt(h.K_total) * h.wmax > 2e-3) ? 4 : 3;
         int dev = 0;
         GML_CUDA(cudaGetDevice(&dev));
         GML_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -757,7 +757,7 @@ struct BackendTC : EvalBackend {
     double grad_noise() const override {
         const Histogram& h = *p.hist;
         const int nr = level == 0 ? std::max(2, nR - 1) : nR;
-        return std::max(1e-9, 0.29 * std::sqrt((double)h.K) * h.wmax * 20.0 / r_qmax(nr));
+        return std::max(1e-9, 0.29 * std::sqrt(h.K_total) * h.wmax * 20.0 / r_qmax(nr));
     }
     // level 0 needs |x| < 1 (checked by the quantiser: an overflow pins the backend to the fine level)
     bool coarse_overflow = false;

@@ -178,6 +178,8 @@ void hist_from_device(Histogram& h, const double* d_counts, const int8_t* d_spin
     GML_REQUIRE((hf & 2) == 0, "histogram counts must be positive and finite");
     h.M = hs[0];
     h.wmax = hs[1] / hs[0];
+    h.M_local = 0.0;
+    h.K_total = (double)K;
 }
 
 void build_multibody_features(Histogram& h, int order, const std::vector<int32_t>& h_subsets, int F,

@@ -48,12 +48,13 @@ mutable struct GMLB200Stats
 end
 
 """
-    B200(; tol=0.0, max_iter=0, solver=:auto, barrier_mu=0.0, device=0, verbose=0)
+    B200(; tol=0.0, max_iter=0, solver=:auto, barrier_mu=0.0, device=0, devices=1, verbose=0)
 
 Batched GPU method.  `tol`: stopping tolerance (max-norm of the proximal-gradient mapping for the
 FISTA solvers, Newton step for the small-problem solver; 0 selects 1e-6 / 1e-12).  `barrier_mu > 0`
 returns the log-barrier point Ipopt stops at instead of the exact L1 minimiser (1e-9 reproduces the
-stored test fixtures to ~1e-9; available for problems with at most 64 features per node).
+stored test fixtures to ~1e-9; available for problems with at most 64 features per node).  `devices > 1` shards
+the node problems over that many GPUs (device, device+1, ...) from this one Julia process.
 """
 mutable struct B200 <: GMLMethod
     tol::Float64
@@ -61,17 +62,19 @@ mutable struct B200 <: GMLMethod
     solver::Symbol
     barrier_mu::Float64
     device::Int
+    devices::Int
     verbose::Int
     stats::GMLB200Stats
 end
-B200(; tol=0.0, max_iter=0, solver=:auto, barrier_mu=0.0, device=0, verbose=0) =
-    B200(tol, max_iter, solver, barrier_mu, device, verbose, GMLB200Stats())
+B200(; tol=0.0, max_iter=0, solver=:auto, barrier_mu=0.0, device=0, devices=1, verbose=0) =
+    B200(tol, max_iter, solver, barrier_mu, device, devices, verbose, GMLB200Stats())
 
 const _gml_b200_solver_id = Dict(:auto => 0, :newton => 1, :fista_cc => 2, :fista_tc => 3)
 
 function _gml_b200_opts(m::B200)
     _GMLB200Opts(m.tol, m.barrier_mu, Int32(m.max_iter), Int32(_gml_b200_solver_id[m.solver]), Int32(m.device),
-                 Int32(0), Int32(0), Int32(m.verbose), C_NULL, ntuple(_ -> Int32(0), 8))
+                 Int32(0), Int32(0), Int32(m.verbose), C_NULL,
+                 (Int32(0), Int32(0), Int32(0), Int32(0), Int32(m.devices), Int32(0), Int32(0), Int32(0)))   # reserved[4] = devices
 end
 
 function _gml_b200_check(rc::Integer)

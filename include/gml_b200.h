@@ -58,7 +58,9 @@ typedef struct gml_b200_opts {
     int32_t reserved[8]; /* reserved[0] != 0: time the contraction kernels with CUDA events (stats.reserved_d);
                             reserved[1] != 0: enable the multilevel (sample-subset) continuation of the FISTA solvers;
                             reserved[2] != 0: sample-sharded solve (see gml_b200_comm_init);
-                            reserved[3] != 0: disable the coarse precision level of the tensor-core FISTA solver */
+                            reserved[3] != 0: disable the coarse precision level of the tensor-core FISTA solver;
+                            reserved[4] > 1: gml_b200_learn_pairwise shards the nodes over that many devices
+                            (device, device+1, ...) from this one process, one host thread per device */
 } gml_b200_opts;
 
 typedef struct gml_b200_stats {
