@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -171,9 +172,9 @@ void finish_stats(gml_b200_stats* stats, const SolveResult& r, int solver_used, 
     for (int i = 0; i < 4; ++i) stats->reserved_d[i] = r.profile[i];
 }
 
-void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, const gml_b200_opts& o, int nb, int ne,
-                         double* d_rows, double* d_obj, gml_b200_stats* stats, cudaStream_t st, double t0,
-                         DevBuf<double>* warm = nullptr /* in: start point (if allocated), out: solution [Nn x Fp] */) {
+void solve_pairwise_rows_one(gml_b200_handle* h, int formulation, double lambda, const gml_b200_opts& o, int nb, int ne,
+                             double* d_rows, double* d_obj, gml_b200_stats* stats, cudaStream_t st, double t0,
+                             DevBuf<double>* warm = nullptr /* in: start point (if allocated), out: solution [Nn x Fp] */) {
     GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
     GML_REQUIRE(formulation >= GML_B200_RISE && formulation <= GML_B200_RPLE, "unknown formulation id");
     GML_REQUIRE(lambda >= 0.0 && std::isfinite(lambda), "lambda must be finite and >= 0");
@@ -209,6 +210,69 @@ void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, con
     finish_stats(stats, r, solver_used, p.Nn, hist.K, solve_ms, 0.0, t0);
     if (r.n_unconverged > 0) {
         set_error("solver did not reach tol within max_iter for " + std::to_string(r.n_unconverged) + " node(s)");
+        throw CudaError{GML_B200_ENOTCONV};
+    }
+}
+
+// Memory-aware front end: the residual limbs of the tensor-core path take nR * nodes * Kp bytes (31 GB at C3 on one
+// GPU).  When a shard would not fit next to the resident histogram copies, its nodes are solved in consecutive
+// chunks (node problems are independent, src/GraphicalModelLearning.jl:161) instead of failing with out-of-memory.
+void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, const gml_b200_opts& o, int nb, int ne,
+                         double* d_rows, double* d_obj, gml_b200_stats* stats, cudaStream_t st, double t0,
+                         DevBuf<double>* warm = nullptr) {
+    GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
+    const Histogram& hist = h->hist;
+    const int N = hist.N;
+    GML_REQUIRE(nb >= 0 && ne <= N && nb < ne, "node shard out of range");
+    const int F = N + 1;
+    int solver = o.solver == GML_B200_SOLVER_AUTO ? (F <= NEWTON_MAX_F ? GML_B200_SOLVER_NEWTON : GML_B200_SOLVER_FISTA_TC) : o.solver;
+    int chunk = ne - nb;
+    if (solver == GML_B200_SOLVER_FISTA_TC && !warm && o.reserved[2] == 0) {
+        size_t free_b = 0, total_b = 0;
+        GML_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const double Kp = (double)hist.Kp, Fp = (double)hist.Fb;
+        const double resident = 3.0 * Kp * Fp + 12.0 * Kp;                        // base, P, Qb, weights
+        double budget = 0.88 * (double)total_b - resident;
+        if (const char* env = std::getenv("GML_B200_MEM_BUDGET_GB")) budget = std::atof(env) * 1e9;   // test hook
+        auto need = [&](int nn) {                                                 // per-solve buffers for nn nodes
+            const double np2 = (double)round_up(nn, 128);
+            return 4.0 * np2 * Kp + 8.0 * 8.0 * np2 * Fp + 7.0 * np2 * Fp;         // R (<= 4 limbs), fp64 state + G64, limb tiles
+        };
+        if (need(chunk) > budget) {
+            chunk = (int)((budget - 0.0) / (need(128) / 128.0)) / 128 * 128;
+            GML_REQUIRE(chunk >= 128, "histogram too large for one GPU even with node chunking: use more GPUs (node shards) or "
+                                      "the sample-sharded mode");
+        }
+    }
+    if (chunk >= ne - nb) {
+        solve_pairwise_rows_one(h, formulation, lambda, o, nb, ne, d_rows, d_obj, stats, st, t0, warm);
+        return;
+    }
+    gml_b200_stats acc{}, cur{};
+    int unconverged = 0;
+    for (int b = nb; b < ne; b += chunk) {
+        const int e = std::min(ne, b + chunk);
+        std::memset(&cur, 0, sizeof(cur));
+        try {
+            solve_pairwise_rows_one(h, formulation, lambda, o, b, e, d_rows + (size_t)(b - nb) * N, d_obj ? d_obj + (b - nb) : nullptr,
+                                    &cur, st, now_ms());
+        } catch (const CudaError& err) {
+            if (err.code != GML_B200_ENOTCONV) throw;
+        }
+        unconverged += cur.n_unconverged;
+        acc.solver_used = cur.solver_used;
+        acc.iterations = std::max(acc.iterations, cur.iterations);
+        acc.n_fg_passes += cur.n_fg_passes; acc.n_f_passes += cur.n_f_passes;
+        acc.evals += cur.evals; acc.solve_ms += cur.solve_ms;
+        acc.max_residual = std::max(acc.max_residual, cur.max_residual);
+        for (int i = 0; i < 4; ++i) acc.reserved_d[i] += cur.reserved_d[i];
+    }
+    acc.n_unconverged = unconverged;
+    acc.kernel_launches = g_launches;
+    acc.total_ms = now_ms() - t0;
+    if (stats) *stats = acc;
+    if (unconverged > 0) {
+        set_error("solver did not reach tol within max_iter for " + std::to_string(unconverged) + " node(s)");
         throw CudaError{GML_B200_ENOTCONV};
     }
 }

@@ -167,3 +167,20 @@ def test_regularisation_path_warm_starts(c2_session):
         assert np.abs(path[i] - cold).max() <= 5e-6
     print("path passes warm", warm_passes, "cold", cold_passes)
     assert warm_passes <= cold_passes + 2
+
+
+def test_node_chunking_when_memory_is_short(monkeypatch):
+    """A shard whose residual-limb buffer would not fit is solved in consecutive node chunks (here forced through the
+    GML_B200_MEM_BUDGET_GB test hook: 300 nodes -> chunks of 128) and must give the same rows."""
+    rng = np.random.default_rng(9)
+    n, k = 300, 50_000
+    spins = rng.choice(np.array([-1, 1], dtype=np.int8), size=(n, k))
+    counts = np.ones(k)
+    sess = gml_b200.Session(0).upload(counts, spins)
+    whole = sess.solve_pairwise(RISE(0.4, False), B200(coarse_level=False))
+    monkeypatch.setenv("GML_B200_MEM_BUDGET_GB", "0.05")
+    m = B200(coarse_level=False)
+    chunked = sess.solve_pairwise(RISE(0.4, False), m)
+    monkeypatch.delenv("GML_B200_MEM_BUDGET_GB")
+    assert m.last_stats["n_fg_passes"] > 0
+    assert np.abs(chunked - whole).max() <= 1e-9
