@@ -13,6 +13,13 @@
 //   * the gradient contraction  G[u,f] = -sum_k r[u,k] S[k,f]  is again an int8 GEMM, split over
 //     sample ranges; partial tiles are combined with int64 atomics, so the result is independent
 //     of the reduction order (bitwise reproducible).
+//   * two precision levels (set_level): the fine level above, and a coarse level (lattice 2^-20,
+//     3 iterate limbs, |x| < 1, one residual limb fewer) used by the FISTA driver far from the
+//     optimum; nodes never retire on the coarse level and (f, G) are refreshed on the switch.
+//
+// Warp roles: warp 0 issues TMA, warp 1 issues tcgen05.mma, the remaining warps (16 in the energy
+// kernel, 4 in the gradient kernel) run the TMEM epilogues; the energy kernel double-buffers its
+// 2 x 256 TMEM columns so the MMA of sample block b+1 overlaps the epilogue of block b.
 //
 // Replaces the per-node JuMP expression evaluation of src/GraphicalModelLearning.jl:162-172 (and
 // :271-281, :309-319, :106-119) for all nodes at once.
