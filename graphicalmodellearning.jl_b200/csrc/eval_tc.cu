@@ -41,9 +41,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -60,11 +57,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
@@ -86,16 +78,38 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, M = 128, K = 32 per instruction
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+// ---- single-issuer roles, warp-converged ---------------------------------------------------------
+// The TMA / MMA roles run with all 32 lanes converged and warp-uniform operands; only the elected lane's
+// instruction takes effect (predicate inside the asm).  Issuing from `if (lane == 0)` instead makes every
+// operand a per-thread value, and ptxas then wraps each UTMALDG / UTCIMMA / UTCBAR in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall (~20 instructions per MMA): measured, that instruction
+// stream -- not the tensor pipe, TMA or the epilogue -- bounded these kernels at 60-78 % tensor activity.
+__device__ __forceinline__ uint32_t elect_one_pred() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
 }
-// all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_expect_tx_if(uint64_t* bar, uint32_t bytes, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_if(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(pred) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, M = 128, K = 32 per instruction
+__device__ __forceinline__ void umma_i8_if(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(pred) : "memory");
+}
+// all previously issued MMAs of the issuing thread arrive on `bar` when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit_if(uint64_t* bar, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(pred) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
     asm volatile(
@@ -141,13 +155,13 @@ __device__ __forceinline__ int balanced_digit(int& q) {   // returns q mod 128 i
 }
 
 
-// x [Nn x Fp] (double, on the lattice) -> limb tiles X [(tile*xl + limb)*64 + i][Fp] and per-node residual scales
+// x [Nn x Fp] (double, on the lattice) -> limb tiles X [(tile*xl + limb)*node_tile + i][Fp] and per-node residual scales
 __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __restrict__ x, int Nn, int Fp, int form, double wmax,
-                                                           int nR, int xl, double inv_lattice, int8_t* __restrict__ X,
+                                                           int nR, int xl, int node_tile, double inv_lattice, int8_t* __restrict__ X,
                                                            float* __restrict__ inv_dr, double* __restrict__ delta /* [Nn_pad]: deltaR */,
                                                            int* __restrict__ flags) {
     const int u = blockIdx.x;
-    const int tile = u / NODE_TILE1, i = u % NODE_TILE1;
+    const int tile = u / node_tile, i = u % node_tile;
     __shared__ double red[4];
     // largest |q| that xl balanced base-128 digits can hold
     const long long qcap = xl == 3 ? 1040000LL : 134000000LL;
@@ -161,8 +175,8 @@ __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __rest
         int d[X_LIMBS_MAX];
         for (int j = xl - 1; j > 0; --j) d[j] = balanced_digit(q);
         d[0] = q;
-        const int64_t row = ((int64_t)tile * xl) * NODE_TILE1 + i;
-        for (int j = 0; j < xl; ++j) X[(row + (int64_t)j * NODE_TILE1) * Fp + f] = (int8_t)d[j];
+        const int64_t row = ((int64_t)tile * xl) * node_tile + i;
+        for (int j = 0; j < xl; ++j) X[(row + (int64_t)j * node_tile) * Fp + f] = (int8_t)d[j];
     }
     for (int o = 16; o; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l1;
@@ -193,7 +207,17 @@ struct EnergyParams {
     const float* w32;
     const float* inv_dr;                   // [Nn_pad1] 1/deltaR
     double* fsum;                          // [Nn_pad1] objective sums
+    int dbg;                               // ablation switches (only in -DGML_TC_ABLATE builds; see GML_DBG)
 };
+
+// Ablation switches for profiling (variant builds with -DGML_TC_ABLATE, env GML_B200_DBG): results are
+// garbage, timings tell which stage of the pipeline bounds a kernel.  1: skip the epilogue math and the
+// R store, 2: do not load the limb tile, 4: no operand loads at all (MMA on stale shared memory).
+#ifdef GML_TC_ABLATE
+#define GML_DBG(p, bit) (((p).dbg & (bit)) != 0)
+#else
+#define GML_DBG(p, bit) false
+#endif
 
 constexpr int E_STAGES = 3;
 #ifndef GML_E_EPI_WARPS
@@ -264,7 +288,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
     float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);   // [64] 1/deltaR of the node tile
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index, uniform for the compiler
     const int kblocks = p.Fp / 128;
     const int n_items = p.n_tiles * p.n_groups;
 
@@ -282,7 +306,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     auto item_range = [&](int item, int& nt, int64_t& b0, int64_t& b1) {
         const int g = item / p.n_tiles;
@@ -292,57 +316,57 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
     };
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int slot = 0; uint32_t sphase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int nt; int64_t b0, b1;
-                item_range(item, nt, b0, b1);
-                for (int64_t eb = b0; eb < b1; ++eb) {
-                    const int64_t sb = eb * p.block_stride;
-                    mbar_wait(&sempty[slot], sphase ^ 1);
-                    mbar_expect_tx(&sfull[slot], E_S_BYTES);
-                    if (p.spin_vec) tma_load_2d(s_spin + slot * E_S_BYTES, &tmSv, &sfull[slot], p.node_begin_row + nt * NODE_TILE1, (int)(sb * 128));
-                    else tma_load_2d(s_spin + slot * E_S_BYTES, &tmS, &sfull[slot], 0, (int)(sb * p.Fspin) + p.node_begin_row + nt * NODE_TILE1);
-                    if (++slot == 2) { slot = 0; sphase ^= 1; }
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], E_A_BYTES + XL * NODE_TILE1 * 128);
-                        uint8_t* a = s_stage + stage * E_STAGE_BYTES;
-                        tma_load_2d(a, &tmA, &full[stage], kb * 128, (int)(sb * 128));
-                        tma_load_2d(a + E_A_BYTES, &tmB, &full[stage], kb * 128, nt * XL * NODE_TILE1);
-                        if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
-                    }
+        // ================= TMA producer (whole warp converged, elected lane issues) =================
+        const uint32_t leader = elect_one_pred();
+        int stage = 0; uint32_t phase = 0;
+        int slot = 0; uint32_t sphase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int nt; int64_t b0, b1;
+            item_range(item, nt, b0, b1);
+            for (int64_t eb = b0; eb < b1; ++eb) {
+                const int64_t sb = eb * p.block_stride;
+                mbar_wait(&sempty[slot], sphase ^ 1);
+                mbar_expect_tx_if(&sfull[slot], E_S_BYTES, leader);
+                if (p.spin_vec) tma_load_2d_if(s_spin + slot * E_S_BYTES, &tmSv, &sfull[slot], p.node_begin_row + nt * NODE_TILE1, (int)(sb * 128), leader);
+                else tma_load_2d_if(s_spin + slot * E_S_BYTES, &tmS, &sfull[slot], 0, (int)(sb * p.Fspin) + p.node_begin_row + nt * NODE_TILE1, leader);
+                if (++slot == 2) { slot = 0; sphase ^= 1; }
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    const uint32_t ld_a = GML_DBG(p, 4) ? 0u : leader, ld_b = GML_DBG(p, 6) ? 0u : leader;
+                    mbar_expect_tx_if(&full[stage], (ld_a ? E_A_BYTES : 0) + (ld_b ? XL * NODE_TILE1 * 128 : 0), leader);
+                    uint8_t* a = s_stage + stage * E_STAGE_BYTES;
+                    tma_load_2d_if(a, &tmA, &full[stage], kb * 128, (int)(sb * 128), ld_a);
+                    tma_load_2d_if(a + E_A_BYTES, &tmB, &full[stage], kb * 128, nt * XL * NODE_TILE1, ld_b);
+                    if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_i8(128, XL * NODE_TILE1);
-            int stage = 0; uint32_t phase = 0;
-            int as = 0; uint32_t aphase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int nt; int64_t b0, b1;
-                item_range(item, nt, b0, b1);
-                for (int64_t sb = b0; sb < b1; ++sb) {
-                    mbar_wait(&tempty[as], aphase ^ 1);
+        // ================= MMA issuer (whole warp converged, elected lane issues) =================
+        const uint32_t leader = elect_one_pred();
+        constexpr uint32_t idesc = make_idesc_i8(128, XL * NODE_TILE1);
+        const uint32_t stage_base = smem_u32(s_stage);
+        int stage = 0; uint32_t phase = 0;
+        int as = 0; uint32_t aphase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int nt; int64_t b0, b1;
+            item_range(item, nt, b0, b1);
+            for (int64_t sb = b0; sb < b1; ++sb) {
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + as * 256;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + as * 256;
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(s_stage + stage * E_STAGE_BYTES);
-                        const uint64_t da = make_kmajor_desc(a_addr), db = make_kmajor_desc(a_addr + E_A_BYTES);
+                    const uint32_t a_addr = stage_base + stage * E_STAGE_BYTES;
+                    const uint64_t da = make_kmajor_desc(a_addr), db = make_kmajor_desc(a_addr + E_A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_i8(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                        umma_commit(&empty[stage]);
-                        if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
-                    }
-                    umma_commit(&tfull[as]);
-                    if (++as == 2) { as = 0; aphase ^= 1; }
+                    for (int k = 0; k < 4; ++k) umma_i8_if(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u, leader);
+                    umma_commit_if(&empty[stage], leader);
+                    if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
                 }
+                umma_commit_if(&tfull[as], leader);
+                if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
     } else {
@@ -352,6 +376,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
         const int row = quarter * 32 + lane;            // sample within the block == TMEM lane
         const int et = threadIdx.x - 64;                // 0..255
         constexpr int NPT = NODE_TILE1 / (E_EPI_WARPS / 4);   // nodes per thread
+        constexpr int ACC_STAGES = 2;
         constexpr int EPI_THREADS = 32 * E_EPI_WARPS;
         float facc[NPT];
         int as = 0; uint32_t aphase = 0;
@@ -386,6 +411,14 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                 mbar_wait(&sfull[slot], sphase);
                 mbar_wait(&tfull[as], aphase);
                 tc_fence_after();
+                if (GML_DBG(p, 1)) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&tempty[as]); mbar_arrive(&sempty[slot]); }
+                    if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+                    if (++slot == 2) { slot = 0; sphase ^= 1; }
+                    continue;
+                }
                 // R staging is double buffered: block b writes buffer b&1 while the TMA store of block b-1 still
                 // reads the other one; the single barrier below also publishes that store b-1 has drained.
                 const uint32_t rb_addr = smem_u32(s_r) + (rbuf ? E_R_BUF_BYTES : 0) + row;
@@ -492,6 +525,7 @@ struct GradParams {
     int n_splits;                 // sample ranges; work item = (split, output tile)
     int64_t sample_blocks, block_stride;   // as in EnergyParams
     long long* G;                 // [Nn_pad2 x Fp] int64
+    int dbg;                      // ablation switches (GML_DBG)
 };
 
 constexpr int G_TILE_BYTES = 128 * 128;
@@ -515,7 +549,7 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
     uint64_t* tfull = bars + 2 * G_STAGES;
     uint64_t* tempty = tfull + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index, uniform for the compiler
 
     const int tiles = p.m_tiles * p.f_tiles;
     const int n_items = tiles * p.n_splits;
@@ -530,7 +564,7 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     auto decode = [&](int item, int& mt, int& ft, int64_t& b0, int64_t& b1) {
         const int ks = item / tiles, r = item % tiles;
@@ -540,52 +574,54 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int mt, ft; int64_t b0, b1;
-                decode(item, mt, ft, b0, b1);
-                for (int64_t eb = b0; eb < b1; ++eb) {
-                    const int64_t b = eb * p.block_stride;
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    uint8_t* s = smem + stage * STAGE_BYTES;
+        // ================= TMA producer (whole warp converged, elected lane issues) =================
+        const uint32_t leader = elect_one_pred();
+        int stage = 0; uint32_t phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int mt, ft; int64_t b0, b1;
+            decode(item, mt, ft, b0, b1);
+            for (int64_t eb = b0; eb < b1; ++eb) {
+                const int64_t b = eb * p.block_stride;
+                mbar_wait(&empty[stage], phase ^ 1);
+                const uint32_t ld = GML_DBG(p, 4) ? 0u : leader;
+                mbar_expect_tx_if(&full[stage], ld ? STAGE_BYTES : 0, leader);
+                uint8_t* s = smem + stage * STAGE_BYTES;
 #pragma unroll
-                    for (int j = 0; j < NR; ++j)
-                        tma_load_2d(s + j * G_TILE_BYTES, &tmRa, &full[stage], 0, (int)((b * NR + j) * p.r_rows_per_limb) + mt * 128);
-                    tma_load_2d(s + NR * G_TILE_BYTES, &tmQ, &full[stage], 0, (int)(b * p.Fp) + ft * 128);
-                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
-                }
+                for (int j = 0; j < NR; ++j)
+                    tma_load_2d_if(s + j * G_TILE_BYTES, &tmRa, &full[stage], 0, (int)((b * NR + j) * p.r_rows_per_limb) + mt * 128, ld);
+                tma_load_2d_if(s + NR * G_TILE_BYTES, &tmQ, &full[stage], 0, (int)(b * p.Fp) + ft * 128, ld);
+                if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_i8(128, 128);
-            int stage = 0; uint32_t phase = 0, aphase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int mt, ft; int64_t b0, b1;
-                decode(item, mt, ft, b0, b1);
-                for (int64_t c0 = b0; c0 < b1; c0 += G_MAX_BLOCKS) {       // sub-chunks bounded by the int32 range
-                    const int64_t c1 = min(c0 + G_MAX_BLOCKS, b1);
-                    mbar_wait(tempty, aphase ^ 1);
+        // ================= MMA issuer (whole warp converged, elected lane issues) =================
+        const uint32_t leader = elect_one_pred();
+        constexpr uint32_t idesc = make_idesc_i8(128, 128);
+        const uint32_t s_base = smem_u32(smem);
+        int stage = 0; uint32_t phase = 0, aphase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int mt, ft; int64_t b0, b1;
+            decode(item, mt, ft, b0, b1);
+            for (int64_t c0 = b0; c0 < b1; c0 += G_MAX_BLOCKS) {       // sub-chunks bounded by the int32 range
+                const int64_t c1 = min(c0 + G_MAX_BLOCKS, b1);
+                mbar_wait(tempty, aphase ^ 1);
+                tc_fence_after();
+                for (int64_t b = c0; b < c1; ++b) {
+                    mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    for (int64_t b = c0; b < c1; ++b) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t s_addr = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint64_t db = make_kmajor_desc(s_addr + NR * G_TILE_BYTES);
+                    const uint32_t s_addr = s_base + stage * STAGE_BYTES;
+                    const uint64_t db = make_kmajor_desc(s_addr + NR * G_TILE_BYTES);
 #pragma unroll
-                        for (int j = 0; j < NR; ++j) {
-                            const uint64_t da = make_kmajor_desc(s_addr + j * G_TILE_BYTES);
+                    for (int j = 0; j < NR; ++j) {
+                        const uint64_t da = make_kmajor_desc(s_addr + j * G_TILE_BYTES);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_i8(tmem_base + j * 128, da + 2 * k, db + 2 * k, idesc, (b > c0 || k) ? 1u : 0u);
-                        }
-                        umma_commit(&empty[stage]);
-                        if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+                        for (int k = 0; k < 4; ++k) umma_i8_if(tmem_base + j * 128, da + 2 * k, db + 2 * k, idesc, (b > c0 || k) ? 1u : 0u, leader);
                     }
-                    umma_commit(tfull);
-                    aphase ^= 1;
+                    umma_commit_if(&empty[stage], leader);
+                    if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
                 }
+                umma_commit_if(tfull, leader);
+                aphase ^= 1;
             }
         }
     } else {
@@ -692,11 +728,11 @@ struct BackendTC : EvalBackend {
 
     BackendTC(const NodeProblem& prob, cudaStream_t st) : p(prob) {
         Histogram& h = *p.hist;
-        Nn_pad1 = (int)round_up(p.Nn, NODE_TILE1);
-        Nn_pad2 = (int)round_up(p.Nn, NODE_TILE2);
         // Residual limbs: the rounding noise of the gradient is ~0.3 sqrt(K) wmax e^B / qmax(nR).  3 limbs
         // (qmax 1e6) keep it below 1e-8 for near-uniform counts; strongly weighted histograms get 4.
         nR = (std::sqrt(h.K_total) * h.wmax > 2e-3) ? 4 : 3;
+        Nn_pad1 = (int)round_up(p.Nn, NODE_TILE1);
+        Nn_pad2 = (int)round_up(p.Nn, NODE_TILE2);
         int dev = 0;
         GML_CUDA(cudaGetDevice(&dev));
         GML_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -812,7 +848,7 @@ struct BackendTC : EvalBackend {
         const Histogram& h = *p.hist;
         const int xl = level == 0 ? 3 : 4;
         const int nr = level == 0 ? std::max(2, nR - 1) : nR;      // residual limbs of this pass
-        tc_quantize_x_kernel<<<Nn_pad1, 128, 0, st>>>(x, p.Nn, p.Fp, p.form, h.wmax, nr, xl, 1.0 / lattice(), xl == 3 ? X3.p : X4.p,
+        tc_quantize_x_kernel<<<Nn_pad1, 128, 0, st>>>(x, p.Nn, p.Fp, p.form, h.wmax, nr, xl, NODE_TILE1, 1.0 / lattice(), xl == 3 ? X3.p : X4.p,
                                                       inv_dr.p, delta.p, flags.p);
         GML_LAUNCHED();
         GML_CUDA(cudaMemsetAsync(fsum.p, 0, sizeof(double) * Nn_pad1, st));
@@ -821,6 +857,8 @@ struct BackendTC : EvalBackend {
         ep.block_stride = stride; ep.sample_blocks = ceil_div(h.Kp / 128, stride); ep.r_rows_per_limb = Nn_pad2; ep.nR = nr; ep.form = p.form; ep.lattice = (float)lattice();
         ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p;
         ep.node_begin_row = first_row; ep.spin_vec = spin_vec ? 1 : 0;
+        const char* dbg_env = std::getenv("GML_B200_DBG");
+        ep.dbg = dbg_env ? std::atoi(dbg_env) : 0;
         ep.n_groups = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / ep.n_tiles, ep.sample_blocks));
         const int grid1 = std::min(n_sms, ep.n_tiles * ep.n_groups);
         const bool rple = p.form == GML_B200_RPLE;
@@ -845,6 +883,7 @@ struct BackendTC : EvalBackend {
             GradParams gp{};
             gp.Fp = p.Fp; gp.m_tiles = Nn_pad2 / 128; gp.f_tiles = p.Fp / 128; gp.nR = nr;
             gp.r_rows_per_limb = Nn_pad2; gp.block_stride = stride; gp.sample_blocks = ceil_div(h.Kp / 128, stride); gp.G = G64.p;
+            gp.dbg = ep.dbg;
             const int tiles = gp.m_tiles * gp.f_tiles;
             gp.n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / tiles, gp.sample_blocks));
             const int grid2 = std::min(n_sms, tiles * gp.n_splits);
