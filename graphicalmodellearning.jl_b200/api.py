@@ -354,11 +354,13 @@ class Session:
                                                     _ptr(g) if want_grad else None))
         return f, g
 
-    def bench_passes(self, formulation, backend: str = "fista_tc", reps: int = 5, node_begin: int = 0, node_end: int = 0):
+    def bench_passes(self, formulation, backend: str = "fista_tc", reps: int = 5, node_begin: int = 0, node_end: int = 0,
+                     coarse: bool = False):
         """Mean device ms of the contraction kernels: dict(energy_full, grad, energy_obj, full_pass_wall)."""
         form_id = {RISE: 0, logRISE: 1, RPLE: 2}[type(formulation)]
         out = np.zeros(4)
         opts = B200(solver=backend)._opts(node_begin, node_end)
+        opts.reserved[5] = 1 if coarse else 0
         _lib.check(self._lib.gml_b200_bench_passes(self._h, form_id, ctypes.byref(opts), reps, _ptr(out)))
         return dict(zip(("energy_full", "grad", "energy_obj", "full_pass_wall"), out.tolist()))
 

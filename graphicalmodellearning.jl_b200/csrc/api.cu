@@ -654,6 +654,7 @@ int gml_b200_bench_passes(gml_b200_handle* h, int32_t formulation, const gml_b20
         const size_t nx = (size_t)p.Nn * p.Fp;
         dx.alloc(nx); df.alloc(p.Nn); dg.alloc(nx);
         GML_CUDA(cudaMemsetAsync(dx.p, 0, sizeof(double) * nx, st));
+        if (o.reserved[5] == 1) be->set_level(0, st);   // time the coarse precision level
         be->eval(dx.p, true, df.p, dg.p, st);    // warm-up
         be->eval(dx.p, false, df.p, nullptr, st);
         be->set_profiling(true);

@@ -111,6 +111,54 @@ __device__ __forceinline__ void umma_commit_if(uint64_t* bar, uint32_t pred) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
                  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(pred) : "memory");
 }
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on one TPC run ONE M = 256 MMA; each CTA stages its own 128
+// rows of A and HALF of B, keeps its own 128 accumulator rows in its own TMEM; the MMA is issued by the leader (rank 0)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default .release.cta semantics: a cluster-scope release costs a MEMBAR per arrive (measured: the top stall
+    // reason of the epilogue warps); what is ordered here are TMEM reads, by tcgen05.wait::ld + fence::before_thread_sync
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory whose bytes are accounted on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair_if(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(pred) : "memory");
+}
+// D[tmem, both CTAs] (+)= A * B, M = 256 (128 rows per CTA), K = 32 per instruction
+__device__ __forceinline__ void umma_i8_pair_if(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t pred) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(pred) : "memory");
+}
+// all previously issued pair MMAs arrive on the barrier at this shared-memory offset in BOTH CTAs when complete
+__device__ __forceinline__ void umma_commit_pair_if(uint64_t* bar, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b16 m;\n\tsetp.ne.b32 q, %1, 0;\n\tmov.b16 m, 3;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -212,7 +260,8 @@ struct EnergyParams {
 
 // Ablation switches for profiling (variant builds with -DGML_TC_ABLATE, env GML_B200_DBG): results are
 // garbage, timings tell which stage of the pipeline bounds a kernel.  1: skip the epilogue math and the
-// R store, 2: do not load the limb tile, 4: no operand loads at all (MMA on stale shared memory).
+// R store, 2: do not load the limb tile, 4: no operand loads at all (MMA on stale shared memory), 8: do not
+// load the histogram tile (energy kernel), 16: issue no MMA (pair energy kernel: epilogue-only time).
 #ifdef GML_TC_ABLATE
 #define GML_DBG(p, bit) (((p).dbg & (bit)) != 0)
 #else
@@ -260,6 +309,72 @@ __device__ __forceinline__ float fast_lg2(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// Per-block epilogue math of one thread: NPT nodes of one sample (TMEM lane).  Reads the XL limb accumulators,
+// recombines them exactly, applies the node sign, evaluates the objective / residual terms, accumulates the
+// objective into facc and (GRAD) writes the NR balanced residual digits of every node to the staging tile at
+// rb_dst (+ node * 128, + limb * E_R_BYTES_PER_LIMB).  `release` is called once, right after the last TMEM read.
+template <int FORM, bool GRAD, int XL, int NR, int NPT, class Release>
+__device__ __forceinline__ void energy_epilogue_math(const EnergyParams& p, uint32_t tbase, uint32_t spin_addr, uint32_t scale_addr,
+                                                     uint32_t rb_dst, float wk, float (&facc)[NPT], Release release) {
+    const float c_arg = -p.lattice * 1.4426950408889634f;      // exp(-t) = ex2(c_arg * s_u * E_int)
+    constexpr int R_BIAS = NR == 2 ? 64 * 129 : (NR == 3 ? 64 * 16513 : 64 * 2113665);
+#pragma unroll
+    for (int c = 0; c < NPT / 16; ++c) {
+        uint32_t sw[4];                       // the 16 spin bytes of this chunk, packed
+        if (p.spin_vec) {
+            const uint4 v = lds128(spin_addr ^ (uint32_t)(c * 16));   // c * 16 stays inside the thread's 64-byte row
+            sw[0] = v.x; sw[1] = v.y; sw[2] = v.z; sw[3] = v.w;
+        } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t b = spin_addr + (c * 16 + 4 * w) * 128;
+                sw[w] = lds_u8(b) | (lds_u8(b + 128) << 8) | (lds_u8(b + 256) << 16) | (lds_u8(b + 384) << 24);
+            }
+        }
+        int32_t a0[16], a1[16], a2[16], a3[16];
+        tmem_ld16(tbase + 0 * NODE_TILE1 + c * 16, a0);
+        tmem_ld16(tbase + 1 * NODE_TILE1 + c * 16, a1);
+        tmem_ld16(tbase + 2 * NODE_TILE1 + c * 16, a2);
+        if (XL == 4) tmem_ld16(tbase + 3 * NODE_TILE1 + c * 16, a3);
+        tmem_ld_wait();
+        if (c == NPT / 16 - 1) release();         // accumulator fully read: hand it back to the MMA warp
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int nit = c * 16 + i;                           // node within this thread's slice
+            // sign bit of s_u (bytes are 0x01 / 0xFF; 0x00 for padding nodes)
+            const uint32_t sgn = ((i & 3) == 3 ? sw[i >> 2] : (sw[i >> 2] << (24 - 8 * (i & 3)))) & 0x80000000u;
+            // recombine the limb sums: exact integers, at most one rounding
+            float e;
+            if (XL == 3) e = __int2float_rn((a0[i] * 128 + a1[i]) * 128 + a2[i]);
+            else e = fmaf(__int2float_rn(a0[i] * 128 + a1[i]), 16384.f, __int2float_rn(a2[i] * 128 + a3[i]));
+            const float es = __uint_as_float(__float_as_uint(e) ^ sgn);        // s_u * E / lattice
+            float fterm, gterm;
+            if (FORM == GML_B200_RPLE) {
+                const float a = -2.f * p.lattice * es;
+                const float ex = fast_ex2(-fabsf(a) * 1.4426950408889634f);
+                fterm = wk * fmaf(fast_lg2(1.f + ex), 0.6931471805599453f, fmaxf(a, 0.f));
+                gterm = __fdividef(2.f * wk * (a > 0.f ? 1.f : ex), 1.f + ex);   // 2 w sigma(-2t)
+            } else {
+                fterm = wk * fast_ex2(fminf(es * c_arg, 115.f));
+                gterm = fterm;
+            }
+            facc[nit] += fterm;
+            if (GRAD) {
+                // r = s_u * gterm in units of the node's residual grid, rounded to nearest, plus the
+                // bias that makes all balanced digits non-negative
+                const float vq = __uint_as_float(__float_as_uint(gterm * lds_f32(scale_addr + 4 * nit)) ^ sgn);
+                int qb;
+                if (NR == 4) qb = __float2int_rn(vq) + R_BIAS;
+                else qb = __float_as_int(vq + 12582912.f) - 0x4B400000 + R_BIAS;      // |vq| < 2^22
+                const uint32_t dst = rb_dst + nit * 128;
+#pragma unroll
+                for (int j = 0; j < NR; ++j)      // limb 0 = most significant digit
+                    sts_u8(dst + j * E_R_BYTES_PER_LIMB, ((qb >> (7 * (NR - 1 - j))) & 127) - 64);
+            }
+        }
+    }
 }
 
 // Work decomposition: item = (sample range g, node tile nt), ordered group-major and dealt round-robin,
@@ -332,7 +447,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                 if (++slot == 2) { slot = 0; sphase ^= 1; }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    const uint32_t ld_a = GML_DBG(p, 4) ? 0u : leader, ld_b = GML_DBG(p, 6) ? 0u : leader;
+                    const uint32_t ld_a = GML_DBG(p, 12) ? 0u : leader, ld_b = GML_DBG(p, 6) ? 0u : leader;
                     mbar_expect_tx_if(&full[stage], (ld_a ? E_A_BYTES : 0) + (ld_b ? XL * NODE_TILE1 * 128 : 0), leader);
                     uint8_t* a = s_stage + stage * E_STAGE_BYTES;
                     tma_load_2d_if(a, &tmA, &full[stage], kb * 128, (int)(sb * 128), ld_a);
@@ -426,70 +541,14 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                 // spins of this thread's nodes: either 16 contiguous bytes of the sample-major tile [128 samples][64 nodes]
                 // or one byte per node at column `row` of the node-major tile [64 nodes][128 samples]
                 const uint32_t spin_base = smem_u32(s_spin) + slot * E_S_BYTES;
-                const uint32_t spin_addr = p.spin_vec ? spin_base + row * NODE_TILE1 + half * NPT : spin_base + half * NPT * 128 + row;
+                const uint32_t spin_addr = p.spin_vec ? spin_base + row * NODE_TILE1 + ((half * NPT) ^ (((row >> 1) & 3) << 4)) : spin_base + half * NPT * 128 + row;
                 const uint32_t scale_addr = smem_u32(s_scale) + 4 * half * NPT;
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256 + half * NPT;
-                const float c_arg = -p.lattice * 1.4426950408889634f;      // exp(-t) = ex2(c_arg * s_u * E_int)
-                constexpr int R_BIAS = NR == 2 ? 64 * 129 : (NR == 3 ? 64 * 16513 : 64 * 2113665);
-#pragma unroll
-                for (int c = 0; c < NPT / 16; ++c) {
-                    uint32_t sw[4];                       // the 16 spin bytes of this chunk, packed
-                    if (p.spin_vec) {
-                        const uint4 v = lds128(spin_addr + c * 16);
-                        sw[0] = v.x; sw[1] = v.y; sw[2] = v.z; sw[3] = v.w;
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) {
-                            const uint32_t b = spin_addr + (c * 16 + 4 * w) * 128;
-                            sw[w] = lds_u8(b) | (lds_u8(b + 128) << 8) | (lds_u8(b + 256) << 16) | (lds_u8(b + 384) << 24);
-                        }
-                    }
-                    int32_t a0[16], a1[16], a2[16], a3[16];
-                    tmem_ld16(tbase + 0 * NODE_TILE1 + c * 16, a0);
-                    tmem_ld16(tbase + 1 * NODE_TILE1 + c * 16, a1);
-                    tmem_ld16(tbase + 2 * NODE_TILE1 + c * 16, a2);
-                    if (XL == 4) tmem_ld16(tbase + 3 * NODE_TILE1 + c * 16, a3);
-                    tmem_ld_wait();
-                    if (c == NPT / 16 - 1) {              // accumulator fully read: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[as]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int nit = c * 16 + i;                           // node within this thread's slice
-                        // sign bit of s_u (bytes are 0x01 / 0xFF; 0x00 for padding nodes)
-                        const uint32_t sgn = ((i & 3) == 3 ? sw[i >> 2] : (sw[i >> 2] << (24 - 8 * (i & 3)))) & 0x80000000u;
-                        // recombine the limb sums: exact integers, at most one rounding
-                        float e;
-                        if (XL == 3) e = __int2float_rn((a0[i] * 128 + a1[i]) * 128 + a2[i]);
-                        else e = fmaf(__int2float_rn(a0[i] * 128 + a1[i]), 16384.f, __int2float_rn(a2[i] * 128 + a3[i]));
-                        const float es = __uint_as_float(__float_as_uint(e) ^ sgn);        // s_u * E / lattice
-                        float fterm, gterm;
-                        if (FORM == GML_B200_RPLE) {
-                            const float a = -2.f * p.lattice * es;
-                            const float ex = fast_ex2(-fabsf(a) * 1.4426950408889634f);
-                            fterm = wk * fmaf(fast_lg2(1.f + ex), 0.6931471805599453f, fmaxf(a, 0.f));
-                            gterm = __fdividef(2.f * wk * (a > 0.f ? 1.f : ex), 1.f + ex);   // 2 w sigma(-2t)
-                        } else {
-                            fterm = wk * fast_ex2(fminf(es * c_arg, 115.f));
-                            gterm = fterm;
-                        }
-                        facc[nit] += fterm;
-                        if (GRAD) {
-                            // r = s_u * gterm in units of the node's residual grid, rounded to nearest, plus the
-                            // bias that makes all balanced digits non-negative
-                            const float vq = __uint_as_float(__float_as_uint(gterm * lds_f32(scale_addr + 4 * nit)) ^ sgn);
-                            int qb;
-                            if (NR == 4) qb = __float2int_rn(vq) + R_BIAS;
-                            else qb = __float_as_int(vq + 12582912.f) - 0x4B400000 + R_BIAS;      // |vq| < 2^22
-                            const uint32_t dst = rb_addr + (half * NPT + nit) * 128;
-#pragma unroll
-                            for (int j = 0; j < NR; ++j)      // limb 0 = most significant digit
-                                sts_u8(dst + j * E_R_BYTES_PER_LIMB, ((qb >> (7 * (NR - 1 - j))) & 127) - 64);
-                        }
-                    }
-                }
+                energy_epilogue_math<FORM, GRAD, XL, NR, NPT>(p, tbase, spin_addr, scale_addr, rb_addr + half * NPT * 128, wk, facc, [&] {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                });
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sempty[slot]);
                 if (GRAD) {
@@ -517,6 +576,259 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
+// GEMM-1, CTA-pair form: the limb tile stays RESIDENT in shared memory
+// ------------------------------------------------------------------------------------------
+// The streaming kernel above re-loads the XL*64 x Fp limb tile (B operand) for every 128-sample block and
+// therefore moves 96-107 bytes of L2 -> shared-memory traffic per SM clock at full tensor rate -- measured, that
+// (not the tensor pipe, not the epilogue) bounds it (profiles/r1_ablation.txt).  Here two CTAs of a cluster pair
+// up (tcgen05 cta_group::2, M = 256 = two 128-sample blocks): each CTA keeps HALF of the limb tile (XL*32 rows x
+// Fp <= 128 KB) resident for a whole work item and streams only its own histogram tiles (16 KB per 128 features),
+// 32-42 bytes per SM clock.  Same epilogue, same results (exact integer energies).
+// Work item = (range of sample-block pairs, node tile); pair-step pb covers blocks 2 pb (rank 0) and 2 pb + 1 (rank 1).
+constexpr int E2_MAX_FP = 1024;                          // resident limb half: XL*32 rows x Fp bytes
+__host__ __device__ constexpr int e2_b_bytes(int xl) { return xl * 32 * E2_MAX_FP; }
+__host__ __device__ constexpr int e2_fixed(int xl, int nr, bool grad, int rbufs) {
+    return e2_b_bytes(xl) + 2 * E_S_BYTES + (grad ? rbufs * nr * E_R_BYTES_PER_LIMB : 0) + 1024 + 512;
+}
+__host__ __device__ constexpr int e2_rbufs(int xl, int nr, bool grad) {
+    return (grad && e2_fixed(xl, nr, grad, 2) + 3 * E_A_BYTES <= 227 * 1024) ? 2 : 1;
+}
+__host__ __device__ constexpr int e2_stages(int xl, int nr, bool grad) {
+    const int room = 227 * 1024 - e2_fixed(xl, nr, grad, e2_rbufs(xl, nr, grad));
+    return room / E_A_BYTES > 6 ? 6 : room / E_A_BYTES;
+}
+__host__ __device__ constexpr int e2_smem(int xl, int nr, bool grad) {
+    return e2_fixed(xl, nr, grad, e2_rbufs(xl, nr, grad)) + e2_stages(xl, nr, grad) * E_A_BYTES;
+}
+
+template <int FORM, bool GRAD, int XL, int NR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(E_THREADS, 1)
+tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp], box {128 features, 128 samples}
+                      const __grid_constant__ CUtensorMap tmBh,   // X  [tiles*XL*64 x Fp], box {128 features, XL*32 rows}
+                      const __grid_constant__ CUtensorMap tmS,    // spins, sample-blocked (see tc_energy_kernel)
+                      const __grid_constant__ CUtensorMap tmSv,   // P, box {64 nodes, 128 samples}
+                      const __grid_constant__ CUtensorMap tmR,    // R  [SB*nR*Nn_pad2 x 128], box 64 rows
+                      EnergyParams p) {
+    constexpr int STAGES = e2_stages(XL, NR, GRAD);
+    constexpr int RBUFS = e2_rbufs(XL, NR, GRAD);
+    constexpr int B_BYTES = e2_b_bytes(XL);
+    constexpr int B_KB_BYTES = XL * 32 * 128;            // one 128-feature slab of the resident half
+    static_assert(STAGES >= 3, "pair energy kernel: not enough shared memory for the histogram ring");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_b = smem;
+    uint8_t* s_a = s_b + B_BYTES;
+    uint8_t* s_spin = s_a + STAGES * E_A_BYTES;
+    uint8_t* s_r = s_spin + 2 * E_S_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + (GRAD ? RBUFS * NR * E_R_BYTES_PER_LIMB : 0));
+    uint64_t* full = bars;                    // [STAGES]  leader: both CTAs' histogram tiles of the stage have landed
+    uint64_t* empty = bars + STAGES;          // [STAGES]  per CTA: the pair MMAs that read the stage are complete
+    uint64_t* tfull = bars + 2 * STAGES;      // [2]       per CTA: accumulator published
+    uint64_t* tempty = tfull + 2;             // [2]       leader: both CTAs' epilogues have drained the accumulator
+    uint64_t* sfull = tempty + 2;             // [2]       per CTA: spin tile landed
+    uint64_t* sempty = sfull + 2;             // [2]
+    uint64_t* bfull = sempty + 2;             // leader: both halves of the limb tile have landed
+    uint64_t* bempty = bfull + 1;             // per CTA: all MMAs of the item are complete, the limb tile may be replaced
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 1);
+    float* s_scale = reinterpret_cast<float*>(tmem_slot + 2);   // [64] 1/deltaR of the node tile
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int kblocks = p.Fp / 128;
+    const int n_items = p.n_tiles * p.n_groups;
+    const int64_t pair_blocks = (p.sample_blocks + 1) / 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * E_EPI_WARPS);
+            mbar_init(&sfull[i], 1); mbar_init(&sempty[i], E_EPI_WARPS);
+        }
+        mbar_init(bfull, 1); mbar_init(bempty, 1);
+        fence_barrier_init();
+        prefetch_tmap(&tmA); prefetch_tmap(&tmBh); prefetch_tmap(&tmS); prefetch_tmap(&tmSv);
+        if (GRAD) prefetch_tmap(&tmR);
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();                       // barriers of both CTAs initialised, TMEM allocated in both
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    auto item_range = [&](int item, int& nt, int64_t& b0, int64_t& b1) {
+        const int g = item / p.n_tiles;
+        nt = item % p.n_tiles;
+        b0 = pair_blocks * g / p.n_groups;
+        b1 = pair_blocks * (g + 1) / p.n_groups;
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer of this CTA (whole warp converged, elected lane issues) =================
+        const uint32_t lane_leader = elect_one_pred();
+        const uint32_t cta_leader = rank == 0 ? lane_leader : 0u;       // expect_tx is posted once, by the leader CTA
+        const uint32_t bfull_leader = mapa_rank(smem_u32(bfull), 0);
+        int stage = 0; uint32_t phase = 0;
+        int slot = 0; uint32_t sphase = 0;
+        uint32_t bphase = 0;
+        for (int item = pair; item < n_items; item += n_pairs) {
+            int nt; int64_t b0, b1;
+            item_range(item, nt, b0, b1);
+            // ---- this CTA's half of the limb tile, resident for the whole item
+            mbar_wait(bempty, bphase ^ 1);
+            mbar_expect_tx_if(bfull, 2u * (uint32_t)(XL * 32) * (uint32_t)p.Fp, cta_leader);
+            for (int kb = 0; kb < kblocks; ++kb)
+                tma_load_2d_pair_if(s_b + kb * B_KB_BYTES, &tmBh, bfull_leader, kb * 128, nt * XL * NODE_TILE1 + (int)rank * XL * 32, lane_leader);
+            bphase ^= 1;
+            for (int64_t pb = b0; pb < b1; ++pb) {
+                const int64_t eb = min(2 * pb + (int64_t)rank, p.sample_blocks - 1);    // an odd tail re-reads the last block (its epilogue is skipped)
+                const int64_t sb = eb * p.block_stride;
+                mbar_wait(&sempty[slot], sphase ^ 1);
+                mbar_expect_tx_if(&sfull[slot], E_S_BYTES, lane_leader);
+                if (p.spin_vec) tma_load_2d_if(s_spin + slot * E_S_BYTES, &tmSv, &sfull[slot], p.node_begin_row + nt * NODE_TILE1, (int)(sb * 128), lane_leader);
+                else tma_load_2d_if(s_spin + slot * E_S_BYTES, &tmS, &sfull[slot], 0, (int)(sb * p.Fspin) + p.node_begin_row + nt * NODE_TILE1, lane_leader);
+                if (++slot == 2) { slot = 0; sphase ^= 1; }
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    const bool no_a = GML_DBG(p, 4);
+                    mbar_expect_tx_if(&full[stage], no_a ? 0 : 2 * E_A_BYTES, cta_leader);
+                    tma_load_2d_pair_if(s_a + stage * E_A_BYTES, &tmA, mapa_rank(smem_u32(&full[stage]), 0), kb * 128, (int)(sb * 128), no_a ? 0u : lane_leader);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: leader CTA only =================
+        if (rank == 0) {
+            const uint32_t lane_leader = elect_one_pred();
+            constexpr uint32_t idesc = make_idesc_i8(256, XL * NODE_TILE1);
+            const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            uint32_t bphase = 0;
+            for (int item = pair; item < n_items; item += n_pairs) {
+                int nt; int64_t b0, b1;
+                item_range(item, nt, b0, b1);
+                mbar_wait(bfull, bphase);
+                tc_fence_after();
+                for (int64_t pb = b0; pb < b1; ++pb) {
+                    mbar_wait(&tempty[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + as * 256;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t da = make_kmajor_desc(a_base + stage * E_A_BYTES), db = make_kmajor_desc(b_base + kb * B_KB_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_i8_pair_if(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u, GML_DBG(p, 16) ? 0u : lane_leader);
+                        umma_commit_pair_if(&empty[stage], lane_leader);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_pair_if(&tfull[as], lane_leader);
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                }
+                umma_commit_pair_if(bempty, lane_leader);
+                bphase ^= 1;
+            }
+        }
+    } else {
+        // ================= epilogue warps of this CTA: its own 128 samples of every pair-step =================
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const int et = threadIdx.x - 64;
+        constexpr int NPT = NODE_TILE1 / (E_EPI_WARPS / 4);
+        constexpr int EPI_THREADS = 32 * E_EPI_WARPS;
+        constexpr int R_BUF_BYTES = NR * E_R_BYTES_PER_LIMB;
+        float facc[NPT];
+        int as = 0; uint32_t aphase = 0;
+        int slot = 0; uint32_t sphase = 0;
+        int rbuf = 0;
+        const uint32_t tempty_leader0 = mapa_rank(smem_u32(&tempty[0]), 0), tempty_leader1 = mapa_rank(smem_u32(&tempty[1]), 0);
+        for (int item = pair; item < n_items; item += n_pairs) {
+            int nt; int64_t b0, b1;
+            item_range(item, nt, b0, b1);
+#pragma unroll
+            for (int i = 0; i < NPT; ++i) facc[i] = 0.f;
+            if (GRAD) {
+                named_bar_sync(1, EPI_THREADS);
+                if (et < NODE_TILE1) s_scale[et] = p.inv_dr[nt * NODE_TILE1 + et];
+                named_bar_sync(1, EPI_THREADS);
+            }
+            int since_flush = 0;
+            auto flush = [&]() {
+#pragma unroll
+                for (int i = 0; i < NPT; ++i) {
+                    double v = (double)facc[i];
+                    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) atomicAdd(p.fsum + (int64_t)nt * NODE_TILE1 + half * NPT + i, v);
+                    facc[i] = 0.f;
+                }
+            };
+            auto block_of = [&](int64_t pb) { return min(2 * pb + (int64_t)rank, p.sample_blocks - 1) * p.block_stride; };
+            float wk_next = b0 < b1 ? __ldg(p.w32 + block_of(b0) * 128 + row) : 0.f;
+            for (int64_t pb = b0; pb < b1; ++pb) {
+                const int64_t eb = 2 * pb + (int64_t)rank;
+                const bool valid = eb < p.sample_blocks;
+                const int64_t sb = block_of(pb);
+                if (since_flush >= 32) { flush(); since_flush = 0; }
+                ++since_flush;
+                const float wk = wk_next;
+                if (pb + 1 < b1) wk_next = __ldg(p.w32 + block_of(pb + 1) * 128 + row);     // in flight during this block's math
+                mbar_wait(&sfull[slot], sphase);
+                mbar_wait(&tfull[as], aphase);
+                tc_fence_after();
+                const uint32_t tempty_leader = as ? tempty_leader1 : tempty_leader0;
+                if (!valid || GML_DBG(p, 1)) {          // the second block of an odd tail: hand everything back unused
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive_cluster(tempty_leader); mbar_arrive(&sempty[slot]); }
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                    if (++slot == 2) { slot = 0; sphase ^= 1; }
+                    continue;
+                }
+                if (GRAD && RBUFS == 1) {               // single staging buffer: the store of the previous block must have read it
+                    if (et == 0) tma_store_wait_read();
+                    named_bar_sync(1, EPI_THREADS);
+                }
+                uint8_t* s_rb = s_r + (rbuf ? R_BUF_BYTES : 0);
+                const uint32_t rb_addr = smem_u32(s_rb) + row;
+                const uint32_t spin_base = smem_u32(s_spin) + slot * E_S_BYTES;
+                const uint32_t spin_addr = p.spin_vec ? spin_base + row * NODE_TILE1 + ((half * NPT) ^ (((row >> 1) & 3) << 4)) : spin_base + half * NPT * 128 + row;
+                const uint32_t scale_addr = smem_u32(s_scale) + 4 * half * NPT;
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256 + half * NPT;
+                energy_epilogue_math<FORM, GRAD, XL, NR, NPT>(p, tbase, spin_addr, scale_addr, rb_addr + half * NPT * 128, wk, facc, [&] {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader);
+                });
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sempty[slot]);
+                if (GRAD) {
+                    fence_proxy_async();
+                    if (RBUFS == 2 && et == 0) tma_store_wait_read();   // store of block b-1 has finished reading the other buffer
+                    named_bar_sync(1, EPI_THREADS);
+                    if (RBUFS == 2) rbuf ^= 1;
+                    if (et == 0) {
+                        for (int j = 0; j < NR; ++j)
+                            tma_store_2d(&tmR, s_rb + j * E_R_BYTES_PER_LIMB, 0,
+                                         (int)((sb * NR + j) * p.r_rows_per_limb) + nt * NODE_TILE1);
+                        tma_store_commit();
+                    }
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+                if (++slot == 2) { slot = 0; sphase ^= 1; }
+            }
+            flush();
+        }
+        if (GRAD && et == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    cluster_sync_all();                       // the peer's shared memory and TMEM stay alive until both CTAs are done
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
 // GEMM-2: gradient contraction, split over sample ranges
 // ------------------------------------------------------------------------------------------
 struct GradParams {
@@ -530,17 +842,22 @@ struct GradParams {
 
 constexpr int G_TILE_BYTES = 128 * 128;
 constexpr int64_t G_MAX_BLOCKS = 1 << 16;   // int32 accumulators: |acc| <= 64 * 128 * blocks < 2^31
-__host__ __device__ constexpr int g_stages(int nr) { return nr >= 4 ? 2 : (nr == 3 ? 3 : 4); }
+// Output tile = 128 nodes x FT features per residual limb, all limbs resident in TMEM (NR * FT <= 512 columns).
+// FT = 256 halves the shared-memory fill traffic per MAC of the R operand (the kernels sit at the L2 -> SM
+// bandwidth, not at the tensor pipe, with 128-wide tiles: ablation in profiles/r1_ablation.txt); it fits for NR = 2.
+__host__ __device__ constexpr int g_stage_bytes(int nr, int ft) { return nr * G_TILE_BYTES + ft * 128; }
+__host__ __device__ constexpr int g_stages(int nr, int ft) { return (210 * 1024) / g_stage_bytes(nr, ft) >= 4 ? 4 : (210 * 1024) / g_stage_bytes(nr, ft); }
 
 // Work decomposition: item = (sample split ks, output tile), split-major and dealt round-robin, one item
 // per CTA when tiles * splits <= #SMs.  All CTAs of a split then sweep the SAME sample blocks in lockstep
 // for different output tiles, so every R / Q operand tile is fetched from HBM once and shared through L2.
-template <int NR>
+template <int NR, int FT>
 __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__ CUtensorMap tmRa,   // R  [SB*nR*Nn_pad2 x 128], box 128 rows, SW128
-                                                        const __grid_constant__ CUtensorMap tmQ,    // Qb [SB*Fp x 128], box 128 rows, SW128
+                                                        const __grid_constant__ CUtensorMap tmQ,    // Qb [SB*Fp x 128], box FT rows, SW128
                                                         GradParams p) {
-    constexpr int STAGE_BYTES = (NR + 1) * G_TILE_BYTES;
-    constexpr int G_STAGES = g_stages(NR);
+    static_assert(NR * FT <= 512, "the limb accumulators must fit the 512 TMEM columns");
+    constexpr int STAGE_BYTES = g_stage_bytes(NR, FT);
+    constexpr int G_STAGES = g_stages(NR, FT);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * STAGE_BYTES);
@@ -589,14 +906,14 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < NR; ++j)
                     tma_load_2d_if(s + j * G_TILE_BYTES, &tmRa, &full[stage], 0, (int)((b * NR + j) * p.r_rows_per_limb) + mt * 128, ld);
-                tma_load_2d_if(s + NR * G_TILE_BYTES, &tmQ, &full[stage], 0, (int)(b * p.Fp) + ft * 128, ld);
+                tma_load_2d_if(s + NR * G_TILE_BYTES, &tmQ, &full[stage], 0, (int)(b * p.Fp) + ft * FT, ld);
                 if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (whole warp converged, elected lane issues) =================
         const uint32_t leader = elect_one_pred();
-        constexpr uint32_t idesc = make_idesc_i8(128, 128);
+        constexpr uint32_t idesc = make_idesc_i8(128, FT);
         const uint32_t s_base = smem_u32(smem);
         int stage = 0; uint32_t phase = 0, aphase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -615,7 +932,7 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
                     for (int j = 0; j < NR; ++j) {
                         const uint64_t da = make_kmajor_desc(s_addr + j * G_TILE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_i8_if(tmem_base + j * 128, da + 2 * k, db + 2 * k, idesc, (b > c0 || k) ? 1u : 0u, leader);
+                        for (int k = 0; k < 4; ++k) umma_i8_if(tmem_base + j * FT, da + 2 * k, db + 2 * k, idesc, (b > c0 || k) ? 1u : 0u, leader);
                     }
                     umma_commit_if(&empty[stage], leader);
                     if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
@@ -635,12 +952,12 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
                 mbar_wait(tfull, aphase);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
-                long long* dst = p.G + ((int64_t)mt * 128 + row) * p.Fp + ft * 128;
+                long long* dst = p.G + ((int64_t)mt * 128 + row) * p.Fp + ft * FT;
 #pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < FT / 16; ++c) {
                     int32_t acc[NR][16];
 #pragma unroll
-                    for (int j = 0; j < NR; ++j) tmem_ld16(tbase + j * 128 + c * 16, acc[j]);
+                    for (int j = 0; j < NR; ++j) tmem_ld16(tbase + j * FT + c * 16, acc[j]);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -723,7 +1040,8 @@ struct BackendTC : EvalBackend {
     const int8_t* spin_blocked = nullptr;
     int Fspin = 0;
     DevBuf<int8_t> base_blocked;
-    CUtensorMap tmA, tmB, tmB3, tmS, tmSv, tmR, tmRa, tmQ;
+    CUtensorMap tmA, tmB, tmB3, tmBh, tmB3h, tmS, tmSv, tmR, tmRa, tmQ, tmQ256;
+    bool pair_ok = false;               // the CTA-pair energy kernel applies (limb half-tile fits: Fp <= E2_MAX_FP)
     bool spin_vec = false;
 
     BackendTC(const NodeProblem& prob, cudaStream_t st) : p(prob) {
@@ -750,6 +1068,9 @@ struct BackendTC : EvalBackend {
         tmA = make_map_2d(P, p.Fp, h.Kp, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         tmB = make_map_2d(X4.p, p.Fp, (uint64_t)Nn_pad1 * 4, 128, 4 * NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_128B);
         tmB3 = make_map_2d(X3.p, p.Fp, (uint64_t)Nn_pad1 * 3, 128, 3 * NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_128B);
+        tmBh = make_map_2d(X4.p, p.Fp, (uint64_t)Nn_pad1 * 4, 128, 4 * 32, CU_TENSOR_MAP_SWIZZLE_128B);
+        tmB3h = make_map_2d(X3.p, p.Fp, (uint64_t)Nn_pad1 * 3, 128, 3 * 32, CU_TENSOR_MAP_SWIZZLE_128B);
+        pair_ok = p.Fp <= E2_MAX_FP && !std::getenv("GML_B200_NO_PAIR");
         // Sample-blocked layouts: every TMA box is one contiguous 8/16 KB chunk (one 2 MB page) instead of
         // 64/128 rows that are Kp bytes apart.
         const uint64_t SB = (uint64_t)(h.Kp / 128);
@@ -766,10 +1087,12 @@ struct BackendTC : EvalBackend {
         }
         GML_REQUIRE(SB * Fspin < (1ull << 31), "problem too large for 32-bit TMA row coordinates: shard the samples");
         tmS = make_map_2d(spin_blocked, 128, SB * Fspin, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
-        tmSv = make_map_2d(P, p.Fp, h.Kp, NODE_TILE1, 128, CU_TENSOR_MAP_SWIZZLE_NONE);
+        // 64B swizzle: 16-byte chunk index ^= (sample >> 1) & 3, so the epilogue's 16-byte loads (64-byte row pitch) are bank-conflict free
+        tmSv = make_map_2d(P, p.Fp, h.Kp, NODE_TILE1, 128, CU_TENSOR_MAP_SWIZZLE_64B);
         tmR = make_map_2d(R.p, 128, SB * nR * Nn_pad2, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
         tmRa = make_map_2d(R.p, 128, SB * nR * Nn_pad2, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         tmQ = make_map_2d(Qb, 128, SB * p.Fp, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+        tmQ256 = make_map_2d(Qb, 128, SB * p.Fp, 128, 256, CU_TENSOR_MAP_SWIZZLE_128B);
         GML_CUDA(cudaMemcpyAsync(&first_row, p.spin_row.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         GML_CUDA(cudaStreamSynchronize(st));
         // vector spin loads need the shard's first spin column 16-byte aligned in P (TMA inner-dimension alignment)
@@ -785,15 +1108,33 @@ struct BackendTC : EvalBackend {
         set_smem(tc_energy_kernel<FORM, false, XL, 2>, E_SMEM);                \
         set_smem(tc_energy_kernel<FORM, true, XL, 2>, E_SMEM);                 \
         set_smem(tc_energy_kernel<FORM, true, XL, 3>, E_SMEM);                 \
-        set_smem(tc_energy_kernel<FORM, true, XL, 4>, E_SMEM)
+        set_smem(tc_energy_kernel<FORM, true, XL, 4>, E_SMEM);                 \
+        set_smem(tc_energy_pair_kernel<FORM, false, XL, 2>, e2_smem(XL, 2, false)); \
+        set_smem(tc_energy_pair_kernel<FORM, true, XL, 2>, e2_smem(XL, 2, true));   \
+        set_smem(tc_energy_pair_kernel<FORM, true, XL, 3>, e2_smem(XL, 3, true));   \
+        set_smem(tc_energy_pair_kernel<FORM, true, XL, 4>, e2_smem(XL, 4, true))
         GML_TC_SET(GML_B200_RISE, 3); GML_TC_SET(GML_B200_RISE, 4);
         GML_TC_SET(GML_B200_RPLE, 3); GML_TC_SET(GML_B200_RPLE, 4);
 #undef GML_TC_SET
-        set_smem(tc_grad_kernel<2>, grad_smem(2));
-        set_smem(tc_grad_kernel<3>, grad_smem(3));
-        set_smem(tc_grad_kernel<4>, grad_smem(4));
+        set_smem(tc_grad_kernel<2, 128>, grad_smem(2, 128));
+        set_smem(tc_grad_kernel<2, 256>, grad_smem(2, 256));
+        set_smem(tc_grad_kernel<3, 128>, grad_smem(3, 128));
+        set_smem(tc_grad_kernel<4, 128>, grad_smem(4, 128));
     }
-    static int grad_smem(int nr) { return g_stages(nr) * (nr + 1) * G_TILE_BYTES + 1024 + 128; }
+    static int grad_smem(int nr, int ft) { return g_stages(nr, ft) * g_stage_bytes(nr, ft) + 1024 + 128; }
+    // Number of sample ranges for `tiles` output tiles on n_sms persistent CTAs: the smallest count from one
+    // wave upwards whose items fill the last wave to >= 96 % (items are dealt round-robin, range-major).
+    static int balanced_splits(int tiles, int n_sms, int64_t max_splits) {
+        const int s0 = std::max(1, n_sms / tiles);
+        int best = s0; double best_eff = 0.0;
+        for (int s = s0; s <= 8 * s0 + 8; ++s) {
+            const int64_t items = (int64_t)tiles * s, waves = ceil_div(items, n_sms);
+            const double eff = (double)items / (double)(waves * n_sms);
+            if (eff > best_eff + 1e-9) { best = s; best_eff = eff; }
+            if (eff >= 0.96) break;
+        }
+        return (int)std::max<int64_t>(1, std::min<int64_t>(best, max_splits));
+    }
 
     double lattice() const override { return level == 0 ? X_LATTICE_COARSE : X_LATTICE_FINE; }
     // rounding noise of a gradient component: ~0.29 sqrt(K) wmax e^B / qmax(nr); e^B ~ 20 as a typical upper value
@@ -859,21 +1200,26 @@ struct BackendTC : EvalBackend {
         ep.node_begin_row = first_row; ep.spin_vec = spin_vec ? 1 : 0;
         const char* dbg_env = std::getenv("GML_B200_DBG");
         ep.dbg = dbg_env ? std::atoi(dbg_env) : 0;
-        ep.n_groups = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / ep.n_tiles, ep.sample_blocks));
-        const int grid1 = std::min(n_sms, ep.n_tiles * ep.n_groups);
+        const bool pair = pair_ok && ep.sample_blocks >= 2;
+        const int n_pairs = n_sms / 2;
+        ep.n_groups = pair ? balanced_splits(ep.n_tiles, n_pairs, (ep.sample_blocks + 1) / 2) : balanced_splits(ep.n_tiles, n_sms, ep.sample_blocks);
+        const int grid1 = pair ? 2 * std::min(n_pairs, ep.n_tiles * ep.n_groups) : std::min(n_sms, ep.n_tiles * ep.n_groups);
         const bool rple = p.form == GML_B200_RPLE;
         span_begin(want_grad ? 0 : 2, st);
-#define GML_TC_ENERGY(FORM, GRAD, XL, NRL, MAPB) \
-        tc_energy_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, MAPB, tmS, tmSv, tmR, ep)
-#define GML_TC_BY_NR(FORM, XL, MAPB)                                                        \
-        do {                                                                                \
-            if (!want_grad) GML_TC_ENERGY(FORM, false, XL, 2, MAPB);                        \
-            else if (nr == 2) GML_TC_ENERGY(FORM, true, XL, 2, MAPB);                       \
-            else if (nr == 3) GML_TC_ENERGY(FORM, true, XL, 3, MAPB);                       \
-            else GML_TC_ENERGY(FORM, true, XL, 4, MAPB);                                    \
+#define GML_TC_ENERGY(FORM, GRAD, XL, NRL, MAPB, MAPBH)                                                                          \
+        do {                                                                                                                      \
+            if (pair) tc_energy_pair_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, e2_smem(XL, NRL, GRAD), st>>>(tmA, MAPBH, tmS, tmSv, tmR, ep); \
+            else tc_energy_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, MAPB, tmS, tmSv, tmR, ep);             \
         } while (0)
-        if (xl == 4) { if (rple) GML_TC_BY_NR(GML_B200_RPLE, 4, tmB); else GML_TC_BY_NR(GML_B200_RISE, 4, tmB); }
-        else { if (rple) GML_TC_BY_NR(GML_B200_RPLE, 3, tmB3); else GML_TC_BY_NR(GML_B200_RISE, 3, tmB3); }
+#define GML_TC_BY_NR(FORM, XL, MAPB, MAPBH)                                                 \
+        do {                                                                                \
+            if (!want_grad) GML_TC_ENERGY(FORM, false, XL, 2, MAPB, MAPBH);                 \
+            else if (nr == 2) GML_TC_ENERGY(FORM, true, XL, 2, MAPB, MAPBH);                \
+            else if (nr == 3) GML_TC_ENERGY(FORM, true, XL, 3, MAPB, MAPBH);                \
+            else GML_TC_ENERGY(FORM, true, XL, 4, MAPB, MAPBH);                             \
+        } while (0)
+        if (xl == 4) { if (rple) GML_TC_BY_NR(GML_B200_RPLE, 4, tmB, tmBh); else GML_TC_BY_NR(GML_B200_RISE, 4, tmB, tmBh); }
+        else { if (rple) GML_TC_BY_NR(GML_B200_RPLE, 3, tmB3, tmB3h); else GML_TC_BY_NR(GML_B200_RISE, 3, tmB3, tmB3h); }
 #undef GML_TC_BY_NR
 #undef GML_TC_ENERGY
         GML_LAUNCHED();
@@ -881,16 +1227,18 @@ struct BackendTC : EvalBackend {
         if (want_grad) {
             GML_CUDA(cudaMemsetAsync(G64.p, 0, sizeof(long long) * Nn_pad2 * p.Fp, st));
             GradParams gp{};
-            gp.Fp = p.Fp; gp.m_tiles = Nn_pad2 / 128; gp.f_tiles = p.Fp / 128; gp.nR = nr;
+            const int ft = (nr == 2 && p.Fp % 256 == 0 && !std::getenv("GML_B200_GRAD_FT128")) ? 256 : 128;   // feature-tile width
+            gp.Fp = p.Fp; gp.m_tiles = Nn_pad2 / 128; gp.f_tiles = p.Fp / ft; gp.nR = nr;
             gp.r_rows_per_limb = Nn_pad2; gp.block_stride = stride; gp.sample_blocks = ceil_div(h.Kp / 128, stride); gp.G = G64.p;
             gp.dbg = ep.dbg;
             const int tiles = gp.m_tiles * gp.f_tiles;
-            gp.n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_sms / tiles, gp.sample_blocks));
+            gp.n_splits = balanced_splits(tiles, n_sms, gp.sample_blocks);
             const int grid2 = std::min(n_sms, tiles * gp.n_splits);
             span_begin(1, st);
-            if (nr == 2) tc_grad_kernel<2><<<grid2, 192, grad_smem(2), st>>>(tmRa, tmQ, gp);
-            else if (nr == 3) tc_grad_kernel<3><<<grid2, 192, grad_smem(3), st>>>(tmRa, tmQ, gp);
-            else tc_grad_kernel<4><<<grid2, 192, grad_smem(4), st>>>(tmRa, tmQ, gp);
+            if (nr == 2 && ft == 256) tc_grad_kernel<2, 256><<<grid2, 192, grad_smem(2, 256), st>>>(tmRa, tmQ256, gp);
+            else if (nr == 2) tc_grad_kernel<2, 128><<<grid2, 192, grad_smem(2, 128), st>>>(tmRa, tmQ, gp);
+            else if (nr == 3) tc_grad_kernel<3, 128><<<grid2, 192, grad_smem(3, 128), st>>>(tmRa, tmQ, gp);
+            else tc_grad_kernel<4, 128><<<grid2, 192, grad_smem(4, 128), st>>>(tmRa, tmQ, gp);
             GML_LAUNCHED();
             span_end(st);
         }

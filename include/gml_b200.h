@@ -60,7 +60,8 @@ typedef struct gml_b200_opts {
                             reserved[2] != 0: sample-sharded solve (see gml_b200_comm_init);
                             reserved[3] != 0: disable the coarse precision level of the tensor-core FISTA solver;
                             reserved[4] > 1: gml_b200_learn_pairwise shards the nodes over that many devices
-                            (device, device+1, ...) from this one process, one host thread per device */
+                            (device, device+1, ...) from this one process, one host thread per device;
+                            reserved[5] == 1: gml_b200_bench_passes times the coarse precision level */
 } gml_b200_opts;
 
 typedef struct gml_b200_stats {
