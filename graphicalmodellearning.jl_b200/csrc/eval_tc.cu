@@ -7,12 +7,14 @@
 //         E[k,u] = sum_f S[k,f] * x_u[f]            (S = +-1 features, int8)
 //     is then four int8 GEMM column groups with int32 accumulation -- no rounding at all.
 //   * the epilogue turns E into t = s_u E, psi = exp(-t) (or the RPLE logistic terms) in fp32, and
-//     quantises  r = s_u w psi  to nR balanced int8 limbs with a per-node scale derived from the
-//     bound |t| <= |x_u|_1; the objective terms are summed in fp32 per thread over <= 32 sample blocks
-//     and then in fp64.
-//   * the gradient contraction  G[u,f] = -sum_k r[u,k] S[k,f]  is again an int8 GEMM, split over
-//     sample ranges; partial tiles are combined with int64 atomics, so the result is independent
-//     of the reduction order (bitwise reproducible).
+//     quantises  r = s_u w psi  with a per-node scale derived from the bound |t| <= |x_u|_1 to the integer
+//     q + BIAS >= 0, stored as nR UNSIGNED base-256 digits (one byte plane per digit, written straight from
+//     the epilogue registers to global memory); the objective terms are summed in fp32 per thread over
+//     <= 32 sample blocks and then in fp64.
+//   * the gradient contraction  G[u,f] = -sum_k r[u,k] S[k,f]  is again an int8 GEMM (u8 digits x s8 spins),
+//     split over sample ranges; the BIAS is removed exactly through the column sums of S (the accumulators
+//     start at -BIAS * colsum[f]); partial tiles are combined with int64 atomics, so the result is
+//     independent of the reduction order (bitwise reproducible).
 //   * two precision levels (set_level): the fine level above, and a coarse level (lattice 2^-20,
 //     3 iterate limbs, |x| < 1, one residual limb fewer) used by the FISTA driver far from the
 //     optimum; nodes never retire on the coarse level and (f, G) are refreshed on the switch.
@@ -55,15 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -167,6 +161,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+// Wait for the outstanding TMEM loads; the registers pass through the statement so that no use of them can be
+// scheduled above the wait (the loads are asynchronous: software-pipelined epilogues keep one chunk in flight).
+__device__ __forceinline__ void tmem_ld_wait_on(int32_t (&v)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
+}
+__device__ __forceinline__ void reg_fence(int32_t (&v)[8]) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {     // non-blocking
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -178,9 +192,9 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// instruction descriptor, kind::i8: D = s32, A = B = s8, both K-major
-__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor, kind::i8: D = s32, A = s8 (or u8), B = s8, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_unsigned = false) {
+    return (2u << 4) | ((a_unsigned ? 0u : 1u) << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -194,7 +208,10 @@ constexpr int X_LIMBS_MAX = 4;
 constexpr int NODE_TILE1 = 64;                   // nodes per energy tile (4 limbs -> N = 256)
 constexpr int NODE_TILE2 = 128;                  // nodes per gradient tile (M = 128)
 
-__host__ __device__ constexpr int r_qmax(int nR) { return nR == 2 ? 8000 : (nR == 3 ? 1020000 : 130000000); }
+// residual grid: |q| <= r_qmax(nR), stored as q + r_bias(nR) in nR unsigned bytes (nR <= 3 round with the
+// magic-number trick, which needs |q| < 2^22)
+__host__ __device__ constexpr int r_qmax(int nR) { return nR == 2 ? 32000 : (nR == 3 ? 4000000 : 1000000000); }
+__host__ __device__ constexpr unsigned r_bias(int nR) { return nR == 2 ? 0x8000u : (nR == 3 ? 0x800000u : 0x80000000u); }
 
 __device__ __forceinline__ int balanced_digit(int& q) {   // returns q mod 128 in [-64, 63], q <- (q - d) / 128
     const int d = ((q + 64) & 127) - 64;
@@ -253,6 +270,7 @@ struct EnergyParams {
     int nR, form;
     float lattice;                         // value of one unit of the combined integer energy
     const float* w32;
+    uint8_t* R;                            // residual digit planes [SB][nR][Nn_pad2][128]
     const float* inv_dr;                   // [Nn_pad1] 1/deltaR
     double* fsum;                          // [Nn_pad1] objective sums
     int dbg;                               // ablation switches (only in -DGML_TC_ABLATE builds; see GML_DBG)
@@ -261,14 +279,15 @@ struct EnergyParams {
 // Ablation switches for profiling (variant builds with -DGML_TC_ABLATE, env GML_B200_DBG): results are
 // garbage, timings tell which stage of the pipeline bounds a kernel.  1: skip the epilogue math and the
 // R store, 2: do not load the limb tile, 4: no operand loads at all (MMA on stale shared memory), 8: do not
-// load the histogram tile (energy kernel), 16: issue no MMA (pair energy kernel: epilogue-only time).
+// load the histogram tile (energy kernel), 16: issue no MMA (pair energy kernel: epilogue-only time), 32: epilogue
+// stops after its TMEM reads, 64: no residual stores.
 #ifdef GML_TC_ABLATE
 #define GML_DBG(p, bit) (((p).dbg & (bit)) != 0)
 #else
 #define GML_DBG(p, bit) false
 #endif
 
-constexpr int E_STAGES = 3;
+constexpr int E_STAGES = 4;
 #ifndef GML_E_EPI_WARPS
 #define GML_E_EPI_WARPS 16   // measured: full pass 4.17 ms (8 warps) -> 3.50 ms (16 warps) at N=1000, K=1e6
 #endif
@@ -276,9 +295,7 @@ constexpr int E_EPI_WARPS = GML_E_EPI_WARPS;         // E_EPI_WARPS/4 per TMEM l
 constexpr int E_THREADS = 64 + 32 * E_EPI_WARPS;
 constexpr int E_A_BYTES = 128 * 128, E_B_BYTES = 256 * 128, E_STAGE_BYTES = E_A_BYTES + E_B_BYTES;
 constexpr int E_S_BYTES = NODE_TILE1 * 128;          // spins tile of the node block
-constexpr int E_R_BYTES_PER_LIMB = NODE_TILE1 * 128; // staging for the R limbs
-constexpr int E_R_BUF_BYTES = 4 * E_R_BYTES_PER_LIMB;   // one staging buffer (up to 4 limbs); two of them, used alternately
-constexpr int E_SMEM = E_STAGES * E_STAGE_BYTES + 2 * E_S_BYTES + 2 * E_R_BUF_BYTES + 1024 /*align*/ + 512 /*barriers, scales*/;
+constexpr int E_SMEM = E_STAGES * E_STAGE_BYTES + 2 * E_S_BYTES + 1024 /*align*/ + 512 /*barriers, scales*/;
 static_assert(E_SMEM <= 227 * 1024, "energy kernel exceeds the shared memory of an SM");
 
 // explicit shared-space accesses (the carved-up dynamic smem pointer is generic to the compiler, which would
@@ -298,7 +315,6 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
 }
-__device__ __forceinline__ void sts_u8(uint32_t a, int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 __device__ __forceinline__ float fast_ex2(float x) {
     float y;
@@ -313,13 +329,15 @@ __device__ __forceinline__ float fast_lg2(float x) {
 
 // Per-block epilogue math of one thread: NPT nodes of one sample (TMEM lane).  Reads the XL limb accumulators,
 // recombines them exactly, applies the node sign, evaluates the objective / residual terms, accumulates the
-// objective into facc and (GRAD) writes the NR balanced residual digits of every node to the staging tile at
-// rb_dst (+ node * 128, + limb * E_R_BYTES_PER_LIMB).  `release` is called once, right after the last TMEM read.
+// objective into facc and (GRAD) writes the NR residual digits (bytes of q + BIAS, most significant first) of every
+// node straight to global memory at rg (+ node * 128, + digit * limb_stride): a warp covers one full 32-byte sector
+// per store, and no staging tile, proxy fence, block barrier or TMA store sits between the epilogue warps and the
+// next block.  `release` is called once, right after the last TMEM read.
 template <int FORM, bool GRAD, int XL, int NR, int NPT, class Release>
 __device__ __forceinline__ void energy_epilogue_math(const EnergyParams& p, uint32_t tbase, uint32_t spin_addr, uint32_t scale_addr,
-                                                     uint32_t rb_dst, float wk, float (&facc)[NPT], Release release) {
+                                                     uint8_t* __restrict__ rg, int64_t limb_stride, float wk, float (&facc)[NPT], Release release) {
     const float c_arg = -p.lattice * 1.4426950408889634f;      // exp(-t) = ex2(c_arg * s_u * E_int)
-    constexpr int R_BIAS = NR == 2 ? 64 * 129 : (NR == 3 ? 64 * 16513 : 64 * 2113665);
+    constexpr unsigned R_BIAS = r_bias(NR);
 #pragma unroll
     for (int c = 0; c < NPT / 16; ++c) {
         uint32_t sw[4];                       // the 16 spin bytes of this chunk, packed
@@ -340,6 +358,7 @@ __device__ __forceinline__ void energy_epilogue_math(const EnergyParams& p, uint
         if (XL == 4) tmem_ld16(tbase + 3 * NODE_TILE1 + c * 16, a3);
         tmem_ld_wait();
         if (c == NPT / 16 - 1) release();         // accumulator fully read: hand it back to the MMA warp
+        if (GML_DBG(p, 32)) { facc[0] += __int_as_float(a0[0] ^ a1[3] ^ a2[7] ^ (XL == 4 ? a3[11] : 0)); continue; }   // ablation: TMEM reads only
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int nit = c * 16 + i;                           // node within this thread's slice
@@ -365,13 +384,13 @@ __device__ __forceinline__ void energy_epilogue_math(const EnergyParams& p, uint
                 // r = s_u * gterm in units of the node's residual grid, rounded to nearest, plus the
                 // bias that makes all balanced digits non-negative
                 const float vq = __uint_as_float(__float_as_uint(gterm * lds_f32(scale_addr + 4 * nit)) ^ sgn);
-                int qb;
-                if (NR == 4) qb = __float2int_rn(vq) + R_BIAS;
-                else qb = __float_as_int(vq + 12582912.f) - 0x4B400000 + R_BIAS;      // |vq| < 2^22
-                const uint32_t dst = rb_dst + nit * 128;
+                unsigned qb;
+                if (NR == 4) qb = (unsigned)__float2int_rn(vq) + R_BIAS;
+                else qb = (unsigned)__float_as_int(vq + 12582912.f) - 0x4B400000u + R_BIAS;      // |vq| < 2^22
+                uint8_t* dst = rg + nit * 128;
 #pragma unroll
-                for (int j = 0; j < NR; ++j)      // limb 0 = most significant digit
-                    sts_u8(dst + j * E_R_BYTES_PER_LIMB, ((qb >> (7 * (NR - 1 - j))) & 127) - 64);
+                for (int j = 0; j < NR; ++j)      // plane 0 = most significant byte
+                    if (!GML_DBG(p, 64) || qb == 0xFFFFFFFFu) dst[j * limb_stride] = (uint8_t)(qb >> (8 * (NR - 1 - j)));
             }
         }
     }
@@ -386,14 +405,12 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                                                                 const __grid_constant__ CUtensorMap tmB,   // X  [tiles*XL*64 x Fp], box XL*64 rows
                                                                 const __grid_constant__ CUtensorMap tmS,   // spins, sample-blocked [SB*Fspin x 128], box 64 rows (row coordinates need no alignment)
                                                                 const __grid_constant__ CUtensorMap tmSv,  // P, box {64 nodes, 128 samples}: used when the shard's first spin column is 16-byte aligned
-                                                                const __grid_constant__ CUtensorMap tmR,   // R  [SB*nR*Nn_pad2 x 128], box 64 rows
                                                                 EnergyParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_stage = smem;
     uint8_t* s_spin = smem + E_STAGES * E_STAGE_BYTES;
-    uint8_t* s_r = s_spin + 2 * E_S_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + 2 * E_R_BUF_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_spin + 2 * E_S_BYTES);
     uint64_t* full = bars;                    // [E_STAGES]
     uint64_t* empty = bars + E_STAGES;        // [E_STAGES]
     uint64_t* tfull = bars + 2 * E_STAGES;    // [2]
@@ -415,7 +432,6 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
         }
         fence_barrier_init();
         prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmS); prefetch_tmap(&tmSv);
-        if (GRAD) prefetch_tmap(&tmR);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -496,7 +512,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
         float facc[NPT];
         int as = 0; uint32_t aphase = 0;
         int slot = 0; uint32_t sphase = 0;
-        int rbuf = 0;
+        const int64_t limb_stride = p.r_rows_per_limb * 128;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int nt; int64_t b0, b1;
             item_range(item, nt, b0, b1);
@@ -534,45 +550,82 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
                     if (++slot == 2) { slot = 0; sphase ^= 1; }
                     continue;
                 }
-                // R staging is double buffered: block b writes buffer b&1 while the TMA store of block b-1 still
-                // reads the other one; the single barrier below also publishes that store b-1 has drained.
-                const uint32_t rb_addr = smem_u32(s_r) + (rbuf ? E_R_BUF_BYTES : 0) + row;
-                uint8_t* s_rb = s_r + (rbuf ? E_R_BUF_BYTES : 0);
+                // residual digits of this thread: R[((sb * NR + digit) * rows + node) * 128 + sample]
+                uint8_t* rg = p.R + ((sb * NR * p.r_rows_per_limb + nt * NODE_TILE1 + half * NPT) * 128 + row);
                 // spins of this thread's nodes: either 16 contiguous bytes of the sample-major tile [128 samples][64 nodes]
                 // or one byte per node at column `row` of the node-major tile [64 nodes][128 samples]
                 const uint32_t spin_base = smem_u32(s_spin) + slot * E_S_BYTES;
                 const uint32_t spin_addr = p.spin_vec ? spin_base + row * NODE_TILE1 + ((half * NPT) ^ (((row >> 1) & 3) << 4)) : spin_base + half * NPT * 128 + row;
                 const uint32_t scale_addr = smem_u32(s_scale) + 4 * half * NPT;
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256 + half * NPT;
-                energy_epilogue_math<FORM, GRAD, XL, NR, NPT>(p, tbase, spin_addr, scale_addr, rb_addr + half * NPT * 128, wk, facc, [&] {
+                energy_epilogue_math<FORM, GRAD, XL, NR, NPT>(p, tbase, spin_addr, scale_addr, rg, limb_stride, wk, facc, [&] {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[as]);
                 });
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sempty[slot]);
-                if (GRAD) {
-                    fence_proxy_async();
-                    if (et == 0) tma_store_wait_read();   // store of block b-1 has finished reading the other buffer
-                    named_bar_sync(1, EPI_THREADS);
-                    rbuf ^= 1;
-                    if (et == 0) {
-                        for (int j = 0; j < NR; ++j)
-                            tma_store_2d(&tmR, s_rb + j * E_R_BYTES_PER_LIMB, 0,
-                                         (int)((sb * NR + j) * p.r_rows_per_limb) + nt * NODE_TILE1);
-                        tma_store_commit();
-                    }
-                }
                 if (++as == 2) { as = 0; aphase ^= 1; }
                 if (++slot == 2) { slot = 0; sphase ^= 1; }
             }
             flush();
         }
-        if (GRAD && et == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Chunked form of the epilogue math for software-pipelined epilogues: 8 nodes of one sample whose XL limb sums
+// are already in registers (a[limb][node]); sw0 / sw1 = the 8 spin bytes.  Same arithmetic as above.
+template <int FORM, bool GRAD, int XL, int NR>
+__device__ __forceinline__ void energy_chunk_math(const EnergyParams& p, int32_t (&a)[4][8], uint32_t sw0, uint32_t sw1, uint32_t scale_addr,
+                                                  uint8_t* __restrict__ rg, int64_t limb_stride, float wk, float* __restrict__ facc, bool store) {
+    const float c_arg = -p.lattice * 1.4426950408889634f;
+    constexpr unsigned R_BIAS = r_bias(NR);
+    if (GML_DBG(p, 32)) { facc[0] += __int_as_float(a[0][0] ^ a[1][3] ^ a[2][7] ^ (XL == 4 ? a[3][5] : 0)); return; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t w = i < 4 ? sw0 : sw1;
+        const uint32_t sgn = ((i & 3) == 3 ? w : (w << (24 - 8 * (i & 3)))) & 0x80000000u;
+        float e;
+        if (XL == 3) e = __int2float_rn((a[0][i] * 128 + a[1][i]) * 128 + a[2][i]);
+        else e = fmaf(__int2float_rn(a[0][i] * 128 + a[1][i]), 16384.f, __int2float_rn(a[2][i] * 128 + a[3][i]));
+        const float es = __uint_as_float(__float_as_uint(e) ^ sgn);
+        float fterm, gterm;
+        if (FORM == GML_B200_RPLE) {
+            const float t2 = -2.f * p.lattice * es;
+            const float ex = fast_ex2(-fabsf(t2) * 1.4426950408889634f);
+            fterm = wk * fmaf(fast_lg2(1.f + ex), 0.6931471805599453f, fmaxf(t2, 0.f));
+            gterm = __fdividef(2.f * wk * (t2 > 0.f ? 1.f : ex), 1.f + ex);
+        } else {
+            fterm = wk * fast_ex2(fminf(es * c_arg, 115.f));
+            gterm = fterm;
+        }
+        facc[i] += fterm;
+        if (GRAD) {
+            const float vq = __uint_as_float(__float_as_uint(gterm * lds_f32(scale_addr + 4 * i)) ^ sgn);
+            unsigned qb;
+            if (NR == 4) qb = (unsigned)__float2int_rn(vq) + R_BIAS;
+            else qb = (unsigned)__float_as_int(vq + 12582912.f) - 0x4B400000u + R_BIAS;
+            uint8_t* dst = rg + i * 128;
+            if (store && !GML_DBG(p, 64)) {
+#pragma unroll
+                for (int j = 0; j < NR; ++j) dst[j * limb_stride] = (uint8_t)(qb >> (8 * (NR - 1 - j)));
+            }
+        }
+    }
+}
+template <int XL>
+__device__ __forceinline__ void epi_issue(uint32_t tchunk, int32_t (&a)[4][8]) {
+#pragma unroll
+    for (int j = 0; j < XL; ++j) tmem_ld8(tchunk + j * NODE_TILE1, a[j]);
+}
+template <int XL>
+__device__ __forceinline__ void epi_wait(int32_t (&a)[4][8]) {
+    tmem_ld_wait_on(a[0]);
+#pragma unroll
+    for (int j = 1; j < XL; ++j) reg_fence(a[j]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -587,19 +640,12 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
 // Work item = (range of sample-block pairs, node tile); pair-step pb covers blocks 2 pb (rank 0) and 2 pb + 1 (rank 1).
 constexpr int E2_MAX_FP = 1024;                          // resident limb half: XL*32 rows x Fp bytes
 __host__ __device__ constexpr int e2_b_bytes(int xl) { return xl * 32 * E2_MAX_FP; }
-__host__ __device__ constexpr int e2_fixed(int xl, int nr, bool grad, int rbufs) {
-    return e2_b_bytes(xl) + 2 * E_S_BYTES + (grad ? rbufs * nr * E_R_BYTES_PER_LIMB : 0) + 1024 + 512;
-}
-__host__ __device__ constexpr int e2_rbufs(int xl, int nr, bool grad) {
-    return (grad && e2_fixed(xl, nr, grad, 2) + 3 * E_A_BYTES <= 227 * 1024) ? 2 : 1;
-}
-__host__ __device__ constexpr int e2_stages(int xl, int nr, bool grad) {
-    const int room = 227 * 1024 - e2_fixed(xl, nr, grad, e2_rbufs(xl, nr, grad));
+__host__ __device__ constexpr int e2_fixed(int xl) { return e2_b_bytes(xl) + 2 * E_S_BYTES + 1024 + 512; }
+__host__ __device__ constexpr int e2_stages(int xl) {
+    const int room = 227 * 1024 - e2_fixed(xl);
     return room / E_A_BYTES > 6 ? 6 : room / E_A_BYTES;
 }
-__host__ __device__ constexpr int e2_smem(int xl, int nr, bool grad) {
-    return e2_fixed(xl, nr, grad, e2_rbufs(xl, nr, grad)) + e2_stages(xl, nr, grad) * E_A_BYTES;
-}
+__host__ __device__ constexpr int e2_smem(int xl) { return e2_fixed(xl) + e2_stages(xl) * E_A_BYTES; }
 
 template <int FORM, bool GRAD, int XL, int NR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(E_THREADS, 1)
@@ -607,10 +653,8 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
                       const __grid_constant__ CUtensorMap tmBh,   // X  [tiles*XL*64 x Fp], box {128 features, XL*32 rows}
                       const __grid_constant__ CUtensorMap tmS,    // spins, sample-blocked (see tc_energy_kernel)
                       const __grid_constant__ CUtensorMap tmSv,   // P, box {64 nodes, 128 samples}
-                      const __grid_constant__ CUtensorMap tmR,    // R  [SB*nR*Nn_pad2 x 128], box 64 rows
                       EnergyParams p) {
-    constexpr int STAGES = e2_stages(XL, NR, GRAD);
-    constexpr int RBUFS = e2_rbufs(XL, NR, GRAD);
+    constexpr int STAGES = e2_stages(XL);
     constexpr int B_BYTES = e2_b_bytes(XL);
     constexpr int B_KB_BYTES = XL * 32 * 128;            // one 128-feature slab of the resident half
     static_assert(STAGES >= 3, "pair energy kernel: not enough shared memory for the histogram ring");
@@ -619,8 +663,7 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
     uint8_t* s_b = smem;
     uint8_t* s_a = s_b + B_BYTES;
     uint8_t* s_spin = s_a + STAGES * E_A_BYTES;
-    uint8_t* s_r = s_spin + 2 * E_S_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_r + (GRAD ? RBUFS * NR * E_R_BYTES_PER_LIMB : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_spin + 2 * E_S_BYTES);
     uint64_t* full = bars;                    // [STAGES]  leader: both CTAs' histogram tiles of the stage have landed
     uint64_t* empty = bars + STAGES;          // [STAGES]  per CTA: the pair MMAs that read the stage are complete
     uint64_t* tfull = bars + 2 * STAGES;      // [2]       per CTA: accumulator published
@@ -648,7 +691,6 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
         mbar_init(bfull, 1); mbar_init(bempty, 1);
         fence_barrier_init();
         prefetch_tmap(&tmA); prefetch_tmap(&tmBh); prefetch_tmap(&tmS); prefetch_tmap(&tmSv);
-        if (GRAD) prefetch_tmap(&tmR);
     }
     if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
     tc_fence_before();
@@ -739,11 +781,10 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
         const int et = threadIdx.x - 64;
         constexpr int NPT = NODE_TILE1 / (E_EPI_WARPS / 4);
         constexpr int EPI_THREADS = 32 * E_EPI_WARPS;
-        constexpr int R_BUF_BYTES = NR * E_R_BYTES_PER_LIMB;
         float facc[NPT];
         int as = 0; uint32_t aphase = 0;
         int slot = 0; uint32_t sphase = 0;
-        int rbuf = 0;
+        const int64_t limb_stride = p.r_rows_per_limb * 128;
         const uint32_t tempty_leader0 = mapa_rank(smem_u32(&tempty[0]), 0), tempty_leader1 = mapa_rank(smem_u32(&tempty[1]), 0);
         for (int item = pair; item < n_items; item += n_pairs) {
             int nt; int64_t b0, b1;
@@ -766,62 +807,119 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
                 }
             };
             auto block_of = [&](int64_t pb) { return min(2 * pb + (int64_t)rank, p.sample_blocks - 1) * p.block_stride; };
+            if (GML_DBG(p, 1)) {                        // ablation: no epilogue, only the barrier hand-shakes
+                for (int64_t pb = b0; pb < b1; ++pb) {
+                    mbar_wait(&sfull[slot], sphase);
+                    mbar_wait(&tfull[as], aphase);
+                    tc_fence_after();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive_cluster(as ? tempty_leader1 : tempty_leader0); mbar_arrive(&sempty[slot]); }
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                    if (++slot == 2) { slot = 0; sphase ^= 1; }
+                }
+                continue;
+            }
+            // Software pipeline over half-blocks (8 of the thread's 16 nodes): the TMEM loads of the next chunk are in
+            // flight while the current chunk is evaluated -- also across block boundaries when the next accumulator is
+            // already published -- so TMEM read latency / bandwidth overlaps the math instead of preceding it.
+            static_assert(NPT == 16, "the pipelined epilogue is written for 16 nodes per thread");
+            if (XL == 4) {
+                // 4-limb passes: plain form (one x16 load group per block); the pipelined form below needs 2 x 32
+                // accumulator registers there, spills, and measured slower (5.6 vs 5.0 ms at K = 2e6)
+                float wk_next = b0 < b1 ? __ldg(p.w32 + block_of(b0) * 128 + row) : 0.f;
+                for (int64_t pb = b0; pb < b1; ++pb) {
+                    const bool valid = 2 * pb + (int64_t)rank < p.sample_blocks;
+                    const int64_t sb = block_of(pb);
+                    if (since_flush >= 32) { flush(); since_flush = 0; }
+                    ++since_flush;
+                    const float wk = wk_next;
+                    if (pb + 1 < b1) wk_next = __ldg(p.w32 + block_of(pb + 1) * 128 + row);
+                    mbar_wait(&sfull[slot], sphase);
+                    mbar_wait(&tfull[as], aphase);
+                    tc_fence_after();
+                    const uint32_t tempty_leader = as ? tempty_leader1 : tempty_leader0;
+                    if (!valid) {                           // the second block of an odd tail: hand everything back unused
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { mbar_arrive_cluster(tempty_leader); mbar_arrive(&sempty[slot]); }
+                    } else {
+                        uint8_t* rg = p.R + ((sb * NR * p.r_rows_per_limb + nt * NODE_TILE1 + half * NPT) * 128 + row);
+                        const uint32_t spin_base = smem_u32(s_spin) + slot * E_S_BYTES;
+                        const uint32_t spin_addr = p.spin_vec ? spin_base + row * NODE_TILE1 + ((half * NPT) ^ (((row >> 1) & 3) << 4)) : spin_base + half * NPT * 128 + row;
+                        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256 + half * NPT;
+                        energy_epilogue_math<FORM, GRAD, XL, NR, NPT>(p, tbase, spin_addr, smem_u32(s_scale) + 4 * half * NPT, rg, limb_stride, wk, facc, [&] {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(tempty_leader);
+                        });
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sempty[slot]);
+                    }
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                    if (++slot == 2) { slot = 0; sphase ^= 1; }
+                }
+                flush();
+                continue;
+            }
+            int32_t ra[4][8], rb[4][8];
+            const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * NPT;
+            const uint32_t scale_addr = smem_u32(s_scale) + 4 * half * NPT;
             float wk_next = b0 < b1 ? __ldg(p.w32 + block_of(b0) * 128 + row) : 0.f;
-            for (int64_t pb = b0; pb < b1; ++pb) {
-                const int64_t eb = 2 * pb + (int64_t)rank;
-                const bool valid = eb < p.sample_blocks;
-                const int64_t sb = block_of(pb);
-                if (since_flush >= 32) { flush(); since_flush = 0; }
-                ++since_flush;
-                const float wk = wk_next;
-                if (pb + 1 < b1) wk_next = __ldg(p.w32 + block_of(pb + 1) * 128 + row);     // in flight during this block's math
+            if (b0 < b1) {
                 mbar_wait(&sfull[slot], sphase);
                 mbar_wait(&tfull[as], aphase);
                 tc_fence_after();
-                const uint32_t tempty_leader = as ? tempty_leader1 : tempty_leader0;
-                if (!valid || GML_DBG(p, 1)) {          // the second block of an odd tail: hand everything back unused
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { mbar_arrive_cluster(tempty_leader); mbar_arrive(&sempty[slot]); }
-                    if (++as == 2) { as = 0; aphase ^= 1; }
-                    if (++slot == 2) { slot = 0; sphase ^= 1; }
-                    continue;
-                }
-                if (GRAD && RBUFS == 1) {               // single staging buffer: the store of the previous block must have read it
-                    if (et == 0) tma_store_wait_read();
-                    named_bar_sync(1, EPI_THREADS);
-                }
-                uint8_t* s_rb = s_r + (rbuf ? R_BUF_BYTES : 0);
-                const uint32_t rb_addr = smem_u32(s_rb) + row;
+                epi_issue<XL>(tlane + as * 256, ra);
+            }
+            for (int64_t pb = b0; pb < b1; ++pb) {
+                const bool valid = 2 * pb + (int64_t)rank < p.sample_blocks;      // false: second block of an odd tail (nothing is stored or summed)
+                const int64_t sb = block_of(pb);
+                if (since_flush >= 32) { flush(); since_flush = 0; }
+                ++since_flush;
+                const float wk = valid ? wk_next : 0.f;
+                if (pb + 1 < b1) wk_next = __ldg(p.w32 + block_of(pb + 1) * 128 + row);
+                uint8_t* rg = p.R + ((sb * NR * p.r_rows_per_limb + nt * NODE_TILE1 + half * NPT) * 128 + row);
                 const uint32_t spin_base = smem_u32(s_spin) + slot * E_S_BYTES;
-                const uint32_t spin_addr = p.spin_vec ? spin_base + row * NODE_TILE1 + ((half * NPT) ^ (((row >> 1) & 3) << 4)) : spin_base + half * NPT * 128 + row;
-                const uint32_t scale_addr = smem_u32(s_scale) + 4 * half * NPT;
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * 256 + half * NPT;
-                energy_epilogue_math<FORM, GRAD, XL, NR, NPT>(p, tbase, spin_addr, scale_addr, rb_addr + half * NPT * 128, wk, facc, [&] {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty_leader);
-                });
+                uint32_t sw[4];
+                if (p.spin_vec) {
+                    const uint4 v = lds128(spin_base + row * NODE_TILE1 + ((half * NPT) ^ (((row >> 1) & 3) << 4)));
+                    sw[0] = v.x; sw[1] = v.y; sw[2] = v.z; sw[3] = v.w;
+                } else {
+                    const uint32_t sa = spin_base + half * NPT * 128 + row;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        sw[w] = lds_u8(sa + 4 * w * 128) | (lds_u8(sa + (4 * w + 1) * 128) << 8) | (lds_u8(sa + (4 * w + 2) * 128) << 16) | (lds_u8(sa + (4 * w + 3) * 128) << 24);
+                }
+                // ---- nodes 0..7 (in ra); nodes 8..15 start loading
+                epi_wait<XL>(ra);
+                epi_issue<XL>(tlane + as * 256 + 8, rb);
+                energy_chunk_math<FORM, GRAD, XL, NR>(p, ra, sw[0], sw[1], scale_addr, rg, limb_stride, wk, facc, valid);
+                // ---- nodes 8..15 (in rb): the accumulator is now fully read
+                epi_wait<XL>(rb);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(as ? tempty_leader1 : tempty_leader0);
+                const int as_n = as ^ 1, slot_n = slot ^ 1;
+                const uint32_t aphase_n = as ? aphase ^ 1 : aphase, sphase_n = slot ? sphase ^ 1 : sphase;
+                bool pre = false;
+                if (pb + 1 < b1) {
+                    pre = __all_sync(0xffffffffu, mbar_test(&tfull[as_n], aphase_n) && mbar_test(&sfull[slot_n], sphase_n));
+                    if (pre) { tc_fence_after(); epi_issue<XL>(tlane + as_n * 256, ra); }
+                }
+                energy_chunk_math<FORM, GRAD, XL, NR>(p, rb, sw[2], sw[3], scale_addr + 32, rg + 8 * 128, limb_stride, wk, facc + 8, valid);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sempty[slot]);
-                if (GRAD) {
-                    fence_proxy_async();
-                    if (RBUFS == 2 && et == 0) tma_store_wait_read();   // store of block b-1 has finished reading the other buffer
-                    named_bar_sync(1, EPI_THREADS);
-                    if (RBUFS == 2) rbuf ^= 1;
-                    if (et == 0) {
-                        for (int j = 0; j < NR; ++j)
-                            tma_store_2d(&tmR, s_rb + j * E_R_BYTES_PER_LIMB, 0,
-                                         (int)((sb * NR + j) * p.r_rows_per_limb) + nt * NODE_TILE1);
-                        tma_store_commit();
-                    }
+                as = as_n; aphase = aphase_n; slot = slot_n; sphase = sphase_n;
+                if (pb + 1 < b1 && !pre) {
+                    mbar_wait(&sfull[slot], sphase);
+                    mbar_wait(&tfull[as], aphase);
+                    tc_fence_after();
+                    epi_issue<XL>(tlane + as * 256, ra);
                 }
-                if (++as == 2) { as = 0; aphase ^= 1; }
-                if (++slot == 2) { slot = 0; sphase ^= 1; }
             }
             flush();
         }
-        if (GRAD && et == 0) tma_store_wait_all();
     }
     tc_fence_before();
     cluster_sync_all();                       // the peer's shared memory and TMEM stay alive until both CTAs are done
@@ -841,7 +939,7 @@ struct GradParams {
 };
 
 constexpr int G_TILE_BYTES = 128 * 128;
-constexpr int64_t G_MAX_BLOCKS = 1 << 16;   // int32 accumulators: |acc| <= 64 * 128 * blocks < 2^31
+constexpr int64_t G_MAX_BLOCKS = 1 << 16;   // int32 accumulators: |acc| <= 255 * 128 * blocks < 2^31
 // Output tile = 128 nodes x FT features per residual limb, all limbs resident in TMEM (NR * FT <= 512 columns).
 // FT = 256 halves the shared-memory fill traffic per MAC of the R operand (the kernels sit at the L2 -> SM
 // bandwidth, not at the tensor pipe, with 128-wide tiles: ablation in profiles/r1_ablation.txt); it fits for NR = 2.
@@ -913,7 +1011,7 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
     } else if (warp == 1) {
         // ================= MMA issuer (whole warp converged, elected lane issues) =================
         const uint32_t leader = elect_one_pred();
-        constexpr uint32_t idesc = make_idesc_i8(128, FT);
+        constexpr uint32_t idesc = make_idesc_i8(128, FT, /*a_unsigned=*/true);     // A = residual digit bytes (u8), B = spins (s8)
         const uint32_t s_base = smem_u32(smem);
         int stage = 0; uint32_t phase = 0, aphase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -963,7 +1061,7 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
                     for (int i = 0; i < 16; ++i) {
                         long long v = 0;
 #pragma unroll
-                        for (int j = 0; j < NR; ++j) v = v * 128 + (long long)acc[j][i];
+                        for (int j = 0; j < NR; ++j) v = v * 256 + (long long)acc[j][i];
                         if (v != 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst + c * 16 + i), (unsigned long long)v);
                     }
                 }
@@ -977,6 +1075,33 @@ __global__ void __launch_bounds__(192, 1) tc_grad_kernel(const __grid_constant__
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Column sums of the +-1 feature matrix over the sample blocks of a pass (every `stride`-th block of the
+// sample-blocked copy Qb [SB][Fp][128]): colsum[f] = sum_k S[k,f].  The residual digits hold q + BIAS, so
+//     sum_k (q_k + BIAS) S[k,f] - BIAS * colsum[f] = sum_k q_k S[k,f]      exactly, in integers.
+constexpr int CS_BLOCKS_PER_CTA = 64;
+__global__ void __launch_bounds__(256) tc_colsum_kernel(const int8_t* __restrict__ Qb, int Fp, int64_t n_blocks, int64_t stride,
+                                                      long long* __restrict__ colsum) {
+    const int f = blockIdx.y * 256 + threadIdx.x;
+    if (f >= Fp) return;
+    const int64_t e0 = (int64_t)blockIdx.x * CS_BLOCKS_PER_CTA, e1 = min(e0 + CS_BLOCKS_PER_CTA, n_blocks);
+    int acc = 0;
+    for (int64_t e = e0; e < e1; ++e) {
+        const int4* row = reinterpret_cast<const int4*>(Qb + ((e * stride) * Fp + f) * 128);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int4 v = __ldg(row + i);
+            acc = __dp4a(v.x, 0x01010101, acc); acc = __dp4a(v.y, 0x01010101, acc);
+            acc = __dp4a(v.z, 0x01010101, acc); acc = __dp4a(v.w, 0x01010101, acc);
+        }
+    }
+    if (acc) atomicAdd(reinterpret_cast<unsigned long long*>(colsum + f), (unsigned long long)(long long)acc);
+}
+// gradient accumulators start at -BIAS * colsum[f] (see above)
+__global__ void tc_grad_init_kernel(long long* __restrict__ G, const long long* __restrict__ colsum, long long bias, int64_t n, int Fp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) G[i] = -bias * colsum[i % Fp];
 }
 
 // int64 sums -> double objective / gradient (and the logRISE normalisation, :279)
@@ -1034,13 +1159,15 @@ struct BackendTC : EvalBackend {
     DevBuf<double> delta;
     DevBuf<double> fsum;
     DevBuf<long long> G64;
+    DevBuf<long long> colsum;           // [Fp] column sums of the feature matrix over the blocks of the current stride
+    int64_t colsum_stride = 0;          // stride colsum was computed for (0 = not yet)
     DevBuf<int> flags;
     const int8_t* P;
     const int8_t* Qb;
     const int8_t* spin_blocked = nullptr;
     int Fspin = 0;
     DevBuf<int8_t> base_blocked;
-    CUtensorMap tmA, tmB, tmB3, tmBh, tmB3h, tmS, tmSv, tmR, tmRa, tmQ, tmQ256;
+    CUtensorMap tmA, tmB, tmB3, tmBh, tmB3h, tmS, tmSv, tmRa, tmQ, tmQ256;
     bool pair_ok = false;               // the CTA-pair energy kernel applies (limb half-tile fits: Fp <= E2_MAX_FP)
     bool spin_vec = false;
 
@@ -1061,6 +1188,7 @@ struct BackendTC : EvalBackend {
         inv_dr.alloc(Nn_pad1); delta.alloc(Nn_pad1);
         fsum.alloc(Nn_pad1);
         G64.alloc((size_t)Nn_pad2 * p.Fp);
+        colsum.alloc(p.Fp);
         flags.alloc(1);
         GML_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int), st));
         // rows of R that belong to padding nodes are never written by GEMM-1 tiles beyond Nn_pad1: clear once
@@ -1089,7 +1217,6 @@ struct BackendTC : EvalBackend {
         tmS = make_map_2d(spin_blocked, 128, SB * Fspin, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
         // 64B swizzle: 16-byte chunk index ^= (sample >> 1) & 3, so the epilogue's 16-byte loads (64-byte row pitch) are bank-conflict free
         tmSv = make_map_2d(P, p.Fp, h.Kp, NODE_TILE1, 128, CU_TENSOR_MAP_SWIZZLE_64B);
-        tmR = make_map_2d(R.p, 128, SB * nR * Nn_pad2, 128, NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_NONE);
         tmRa = make_map_2d(R.p, 128, SB * nR * Nn_pad2, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         tmQ = make_map_2d(Qb, 128, SB * p.Fp, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         tmQ256 = make_map_2d(Qb, 128, SB * p.Fp, 128, 256, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1109,10 +1236,10 @@ struct BackendTC : EvalBackend {
         set_smem(tc_energy_kernel<FORM, true, XL, 2>, E_SMEM);                 \
         set_smem(tc_energy_kernel<FORM, true, XL, 3>, E_SMEM);                 \
         set_smem(tc_energy_kernel<FORM, true, XL, 4>, E_SMEM);                 \
-        set_smem(tc_energy_pair_kernel<FORM, false, XL, 2>, e2_smem(XL, 2, false)); \
-        set_smem(tc_energy_pair_kernel<FORM, true, XL, 2>, e2_smem(XL, 2, true));   \
-        set_smem(tc_energy_pair_kernel<FORM, true, XL, 3>, e2_smem(XL, 3, true));   \
-        set_smem(tc_energy_pair_kernel<FORM, true, XL, 4>, e2_smem(XL, 4, true))
+        set_smem(tc_energy_pair_kernel<FORM, false, XL, 2>, e2_smem(XL));           \
+        set_smem(tc_energy_pair_kernel<FORM, true, XL, 2>, e2_smem(XL));            \
+        set_smem(tc_energy_pair_kernel<FORM, true, XL, 3>, e2_smem(XL));            \
+        set_smem(tc_energy_pair_kernel<FORM, true, XL, 4>, e2_smem(XL))
         GML_TC_SET(GML_B200_RISE, 3); GML_TC_SET(GML_B200_RISE, 4);
         GML_TC_SET(GML_B200_RPLE, 3); GML_TC_SET(GML_B200_RPLE, 4);
 #undef GML_TC_SET
@@ -1196,10 +1323,11 @@ struct BackendTC : EvalBackend {
         EnergyParams ep{};
         ep.Kp = h.Kp; ep.Fp = p.Fp; ep.Fspin = Fspin; ep.Nn = p.Nn; ep.n_tiles = Nn_pad1 / NODE_TILE1;
         ep.block_stride = stride; ep.sample_blocks = ceil_div(h.Kp / 128, stride); ep.r_rows_per_limb = Nn_pad2; ep.nR = nr; ep.form = p.form; ep.lattice = (float)lattice();
-        ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p;
+        ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p; ep.R = reinterpret_cast<uint8_t*>(R.p);
         ep.node_begin_row = first_row; ep.spin_vec = spin_vec ? 1 : 0;
         const char* dbg_env = std::getenv("GML_B200_DBG");
         ep.dbg = dbg_env ? std::atoi(dbg_env) : 0;
+
         const bool pair = pair_ok && ep.sample_blocks >= 2;
         const int n_pairs = n_sms / 2;
         ep.n_groups = pair ? balanced_splits(ep.n_tiles, n_pairs, (ep.sample_blocks + 1) / 2) : balanced_splits(ep.n_tiles, n_sms, ep.sample_blocks);
@@ -1208,8 +1336,8 @@ struct BackendTC : EvalBackend {
         span_begin(want_grad ? 0 : 2, st);
 #define GML_TC_ENERGY(FORM, GRAD, XL, NRL, MAPB, MAPBH)                                                                          \
         do {                                                                                                                      \
-            if (pair) tc_energy_pair_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, e2_smem(XL, NRL, GRAD), st>>>(tmA, MAPBH, tmS, tmSv, tmR, ep); \
-            else tc_energy_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, MAPB, tmS, tmSv, tmR, ep);             \
+            if (pair) tc_energy_pair_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, e2_smem(XL), st>>>(tmA, MAPBH, tmS, tmSv, ep); \
+            else tc_energy_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, MAPB, tmS, tmSv, ep);             \
         } while (0)
 #define GML_TC_BY_NR(FORM, XL, MAPB, MAPBH)                                                 \
         do {                                                                                \
@@ -1225,7 +1353,18 @@ struct BackendTC : EvalBackend {
         GML_LAUNCHED();
         span_end(st);
         if (want_grad) {
-            GML_CUDA(cudaMemsetAsync(G64.p, 0, sizeof(long long) * Nn_pad2 * p.Fp, st));
+            if (colsum_stride != stride) {
+                GML_CUDA(cudaMemsetAsync(colsum.p, 0, sizeof(long long) * p.Fp, st));
+                const int64_t nb = ceil_div(h.Kp / 128, stride);
+                tc_colsum_kernel<<<dim3((unsigned)ceil_div(nb, CS_BLOCKS_PER_CTA), (unsigned)ceil_div(p.Fp, 256)), 256, 0, st>>>(Qb, p.Fp, nb, stride, colsum.p);
+                GML_LAUNCHED();
+                colsum_stride = stride;
+            }
+            {
+                const int64_t n = (int64_t)Nn_pad2 * p.Fp;
+                tc_grad_init_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(G64.p, colsum.p, (long long)r_bias(nr), n, p.Fp);
+                GML_LAUNCHED();
+            }
             GradParams gp{};
             const int ft = (nr == 2 && p.Fp % 256 == 0 && !std::getenv("GML_B200_GRAD_FT128")) ? 256 : 128;   // feature-tile width
             gp.Fp = p.Fp; gp.m_tiles = Nn_pad2 / 128; gp.f_tiles = p.Fp / ft; gp.nR = nr;

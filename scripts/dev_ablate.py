@@ -18,6 +18,6 @@ sess = gml_b200.Session(0).attach_device(counts.data_ptr(), spins.data_ptr(), k,
 fl = 2.0 * k * (n + 1) * n
 for dbg in [int(a) for a in (sys.argv[4].split(",") if len(sys.argv) > 4 else "0,1,2,8,4,5".split(","))]:
     os.environ["GML_B200_DBG"] = str(dbg)
-    for coarse in (False, True):
+    for coarse in ((True,) if os.environ.get('LEVELS') == 'coarse' else (False, True)):
         r = sess.bench_passes(gml_b200.RISE(), "fista_tc", reps, coarse=coarse)
         print(f"dbg={dbg} {'coarse' if coarse else 'fine  '}: " + "  ".join(f"{a} {b:.3f} ms ({fl / b / 1e9:.0f} TF/s alg)" for a, b in list(r.items())[:3]), flush=True)
