@@ -85,6 +85,7 @@ class B200(GMLMethod):
     sample_sharded: bool = False  # histogram rows split over ranks, NCCL all-reduce per pass (Session.comm_init)
     coarse_level: bool = True     # fista_tc: 3-limb iterate / one residual limb less while far from convergence
     devices: int = 1              # one-shot learn(): shard the nodes over this many GPUs from this process
+    compaction: bool = True       # FISTA: restrict the passes to the nodes that are still active (parked / converged ones drop out)
     last_stats: dict = field(default_factory=dict, repr=False, compare=False)
 
     def _opts(self, node_begin: int = 0, node_end: int = 0, stream: int = 0) -> _lib.Opts:
@@ -102,6 +103,7 @@ class B200(GMLMethod):
         o.reserved[2] = 1 if self.sample_sharded else 0
         o.reserved[3] = 0 if self.coarse_level else 1
         o.reserved[4] = int(self.devices)
+        o.reserved[6] = 0 if self.compaction else 1
         return o
 
 

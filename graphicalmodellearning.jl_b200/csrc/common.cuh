@@ -169,6 +169,10 @@ struct EvalBackend {
     // Restrict the passes to every `stride`-th block of 128 samples; returns the weight mass rho of the
     // subset (sum of w over the used samples), or a negative value when the backend cannot subsample.
     virtual double set_subsample(int64_t /*stride*/, cudaStream_t) { return -1.0; }
+    // Restrict the following passes to the nodes d_idx[0..n) (device array, entries < 0 = empty slot); nullptr = the
+    // whole shard.  Outputs of nodes outside the list are left untouched.  Returns false when the backend always
+    // evaluates every node (the call is then a no-op).
+    virtual bool set_active(const int* /*d_idx*/, int /*n*/, cudaStream_t) { return false; }
     virtual void set_profiling(bool) {}
     virtual void collect_profile(double* /*out4*/) {}
 };

@@ -224,15 +224,17 @@ __device__ __forceinline__ int balanced_digit(int& q) {   // returns q mod 128 i
 __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __restrict__ x, int Nn, int Fp, int form, double wmax,
                                                            int nR, int xl, int node_tile, double inv_lattice, int8_t* __restrict__ X,
                                                            float* __restrict__ inv_dr, double* __restrict__ delta /* [Nn_pad]: deltaR */,
-                                                           int* __restrict__ flags) {
-    const int u = blockIdx.x;
-    const int tile = u / node_tile, i = u % node_tile;
+                                                           int* __restrict__ flags, const int* __restrict__ act_idx /* slot -> node, or null */) {
+    const int slot = blockIdx.x;
+    const int tile = slot / node_tile, i = slot % node_tile;
+    const int u = (slot < Nn) ? (act_idx ? act_idx[slot] : slot) : Nn;          // Nn here = number of slots in use; padding slots hold x = 0
+    const bool live = slot < Nn && u >= 0;
     __shared__ double red[4];
     // largest |q| that xl balanced base-128 digits can hold
     const long long qcap = xl == 3 ? 1040000LL : 134000000LL;
     double l1 = 0.0;
     for (int f = threadIdx.x; f < Fp; f += blockDim.x) {
-        const double v = (u < Nn) ? x[(int64_t)u * Fp + f] : 0.0;
+        const double v = live ? x[(int64_t)u * Fp + f] : 0.0;
         l1 += fabs(v);
         long long ql = llrint(v * inv_lattice);
         if (ql > qcap || ql < -qcap) { atomicOr(flags, xl == 3 ? 2 : 1); ql = ql > 0 ? qcap : -qcap; }
@@ -251,8 +253,8 @@ __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __rest
         // residual bound: RISE/logRISE  w e^{-t} <= wmax e^B;  RPLE  2 w sigma(-2t) <= 2 wmax
         const double top = (form == GML_B200_RPLE) ? 2.0 * wmax : wmax * exp(fmin(B, 80.0));
         const float inv = (float)(r_qmax(nR) / (top * 1.000001));
-        inv_dr[u] = inv;
-        delta[u] = 1.0 / (double)inv;   // exact reciprocal of what the epilogue multiplies with
+        inv_dr[slot] = inv;
+        delta[slot] = 1.0 / (double)inv;   // exact reciprocal of what the epilogue multiplies with
     }
 }
 
@@ -1105,15 +1107,46 @@ __global__ void tc_grad_init_kernel(long long* __restrict__ G, const long long* 
 }
 
 // int64 sums -> double objective / gradient (and the logRISE normalisation, :279)
-__global__ void tc_finalize_kernel(int form, int Nn, int Fp, const double* __restrict__ fsum,
+__global__ void tc_finalize_kernel(int form, int Fp, const double* __restrict__ fsum,
                                    const long long* __restrict__ G64, const double* __restrict__ delta,
-                                   double* __restrict__ f_out, double* __restrict__ g_out, int want_grad) {
-    const int u = blockIdx.x;
-    const double fs = fsum[u];
+                                   double* __restrict__ f_out, double* __restrict__ g_out, int want_grad,
+                                   const int* __restrict__ act_idx /* slot -> node, or null */) {
+    const int slot = blockIdx.x;
+    const int u = act_idx ? act_idx[slot] : slot;
+    if (u < 0) return;
+    const double fs = fsum[slot];
     if (threadIdx.x == 0) f_out[u] = (form == GML_B200_LOGRISE) ? log(fs) : fs;
     if (!want_grad) return;
-    const double sc = -delta[u] / (form == GML_B200_LOGRISE ? fs : 1.0);
-    for (int f = threadIdx.x; f < Fp; f += blockDim.x) g_out[(int64_t)u * Fp + f] = sc * (double)G64[(int64_t)u * Fp + f];
+    const double sc = -delta[slot] / (form == GML_B200_LOGRISE ? fs : 1.0);
+    for (int f = threadIdx.x; f < Fp; f += blockDim.x) g_out[(int64_t)u * Fp + f] = sc * (double)G64[(int64_t)slot * Fp + f];
+}
+
+// Active-set compaction: sample-major spin matrix of the active nodes only, P_act[k][slot] = s_{idx[slot]}[k]
+// (columns >= n hold 0), the source of the epilogue's spin tiles while a compacted node list is in force.
+__global__ void __launch_bounds__(256) tc_gather_spins_kernel(const int8_t* __restrict__ base, int64_t Kp, const int32_t* __restrict__ spin_row,
+                                                            const int* __restrict__ act_idx, int n, int cap, int8_t* __restrict__ P_act) {
+    __shared__ int8_t tile[64][128 + 16];
+    const int64_t k0 = (int64_t)blockIdx.x * 128;
+    const int j0 = blockIdx.y * 64;
+    for (int r = threadIdx.x >> 3; r < 64; r += 32) {
+        const int j = j0 + r;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (j < n && act_idx[j] >= 0) v = *reinterpret_cast<const int4*>(base + (int64_t)spin_row[act_idx[j]] * Kp + k0 + (threadIdx.x & 7) * 16);
+        *reinterpret_cast<int4*>(&tile[r][(threadIdx.x & 7) * 16]) = v;
+    }
+    __syncthreads();
+    const int s = threadIdx.x >> 1, h = threadIdx.x & 1;
+    uint32_t out[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v |= (uint32_t)(uint8_t)tile[h * 32 + w * 4 + b][s] << (8 * b);
+        out[w] = v;
+    }
+    int4* dst = reinterpret_cast<int4*>(P_act + (k0 + s) * cap + j0 + h * 32);
+    dst[0] = make_int4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_int4(out[4], out[5], out[6], out[7]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1162,6 +1195,11 @@ struct BackendTC : EvalBackend {
     DevBuf<long long> colsum;           // [Fp] column sums of the feature matrix over the blocks of the current stride
     int64_t colsum_stride = 0;          // stride colsum was computed for (0 = not yet)
     DevBuf<int> flags;
+    // active-set compaction (set_active): slot -> node list, spins of the listed nodes, their TMA map
+    const int* act_idx = nullptr;
+    int n_act = 0;
+    DevBuf<int8_t> P_act;
+    CUtensorMap tmSvAct;
     const int8_t* P;
     const int8_t* Qb;
     const int8_t* spin_blocked = nullptr;
@@ -1292,13 +1330,13 @@ struct BackendTC : EvalBackend {
     std::vector<Span> spans;
     void set_profiling(bool on) override { profiling = on; }
     void span_begin(int kind, cudaStream_t st) {
-        if (!profiling || stride != 1) return;   // only full-histogram launches are timed
+        if (!profiling || stride != 1 || act_idx) return;   // only launches over the whole histogram and the whole shard are timed
         Span s; s.kind = kind;
         GML_CUDA(cudaEventCreate(&s.a)); GML_CUDA(cudaEventCreate(&s.b));
         GML_CUDA(cudaEventRecord(s.a, st));
         spans.push_back(s);
     }
-    void span_end(cudaStream_t st) { if (profiling && stride == 1) GML_CUDA(cudaEventRecord(spans.back().b, st)); }
+    void span_end(cudaStream_t st) { if (profiling && stride == 1 && !act_idx) GML_CUDA(cudaEventRecord(spans.back().b, st)); }
     void collect_profile(double* out) override {
         for (auto& s : spans) {
             float ms = 0.f;
@@ -1312,19 +1350,36 @@ struct BackendTC : EvalBackend {
     }
     ~BackendTC() override { for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); } }
 
+    // Restrict the following passes to the listed nodes (slot j evaluates node d_idx[j]; entries < 0 are empty
+    // slots); nullptr restores the full shard.  The work of a pass scales with the padded list length.
+    bool set_active(const int* d_idx, int n, cudaStream_t st) override {
+        if (!d_idx || n <= 0 || n >= p.Nn) { act_idx = nullptr; n_act = 0; return true; }
+        const Histogram& h = *p.hist;
+        const int cap = (int)round_up(n, NODE_TILE2);
+        P_act.alloc((size_t)h.Kp * cap);
+        tc_gather_spins_kernel<<<dim3((unsigned)(h.Kp / 128), (unsigned)(cap / 64)), 256, 0, st>>>(h.base.p, h.Kp, p.spin_row.p, d_idx, n, cap, P_act.p);
+        GML_LAUNCHED();
+        tmSvAct = make_map_2d(P_act.p, cap, h.Kp, NODE_TILE1, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+        act_idx = d_idx; n_act = n;
+        return true;
+    }
+
     void eval(const double* x, bool want_grad, double* f_out, double* g_out, cudaStream_t st) override {
         const Histogram& h = *p.hist;
         const int xl = level == 0 ? 3 : 4;
         const int nr = level == 0 ? std::max(2, nR - 1) : nR;      // residual limbs of this pass
-        tc_quantize_x_kernel<<<Nn_pad1, 128, 0, st>>>(x, p.Nn, p.Fp, p.form, h.wmax, nr, xl, NODE_TILE1, 1.0 / lattice(), xl == 3 ? X3.p : X4.p,
-                                                      inv_dr.p, delta.p, flags.p);
+        const int n_nodes = act_idx ? n_act : p.Nn;                // slots of this pass
+        const int pad1 = (int)round_up(n_nodes, NODE_TILE1), pad2 = (int)round_up(n_nodes, NODE_TILE2);
+        tc_quantize_x_kernel<<<pad1, 128, 0, st>>>(x, n_nodes, p.Fp, p.form, h.wmax, nr, xl, NODE_TILE1, 1.0 / lattice(), xl == 3 ? X3.p : X4.p,
+                                                   inv_dr.p, delta.p, flags.p, act_idx);
         GML_LAUNCHED();
-        GML_CUDA(cudaMemsetAsync(fsum.p, 0, sizeof(double) * Nn_pad1, st));
+        GML_CUDA(cudaMemsetAsync(fsum.p, 0, sizeof(double) * pad1, st));
         EnergyParams ep{};
-        ep.Kp = h.Kp; ep.Fp = p.Fp; ep.Fspin = Fspin; ep.Nn = p.Nn; ep.n_tiles = Nn_pad1 / NODE_TILE1;
+        ep.Kp = h.Kp; ep.Fp = p.Fp; ep.Fspin = Fspin; ep.Nn = n_nodes; ep.n_tiles = pad1 / NODE_TILE1;
         ep.block_stride = stride; ep.sample_blocks = ceil_div(h.Kp / 128, stride); ep.r_rows_per_limb = Nn_pad2; ep.nR = nr; ep.form = p.form; ep.lattice = (float)lattice();
         ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p; ep.R = reinterpret_cast<uint8_t*>(R.p);
-        ep.node_begin_row = first_row; ep.spin_vec = spin_vec ? 1 : 0;
+        ep.node_begin_row = act_idx ? 0 : first_row; ep.spin_vec = (act_idx || spin_vec) ? 1 : 0;
+        const CUtensorMap& tmSvUse = act_idx ? tmSvAct : tmSv;
         const char* dbg_env = std::getenv("GML_B200_DBG");
         ep.dbg = dbg_env ? std::atoi(dbg_env) : 0;
 
@@ -1336,8 +1391,8 @@ struct BackendTC : EvalBackend {
         span_begin(want_grad ? 0 : 2, st);
 #define GML_TC_ENERGY(FORM, GRAD, XL, NRL, MAPB, MAPBH)                                                                          \
         do {                                                                                                                      \
-            if (pair) tc_energy_pair_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, e2_smem(XL), st>>>(tmA, MAPBH, tmS, tmSv, ep); \
-            else tc_energy_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, MAPB, tmS, tmSv, ep);             \
+            if (pair) tc_energy_pair_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, e2_smem(XL), st>>>(tmA, MAPBH, tmS, tmSvUse, ep); \
+            else tc_energy_kernel<FORM, GRAD, XL, NRL><<<grid1, E_THREADS, E_SMEM, st>>>(tmA, MAPB, tmS, tmSvUse, ep);             \
         } while (0)
 #define GML_TC_BY_NR(FORM, XL, MAPB, MAPBH)                                                 \
         do {                                                                                \
@@ -1361,13 +1416,13 @@ struct BackendTC : EvalBackend {
                 colsum_stride = stride;
             }
             {
-                const int64_t n = (int64_t)Nn_pad2 * p.Fp;
+                const int64_t n = (int64_t)pad2 * p.Fp;
                 tc_grad_init_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(G64.p, colsum.p, (long long)r_bias(nr), n, p.Fp);
                 GML_LAUNCHED();
             }
             GradParams gp{};
             const int ft = (nr == 2 && p.Fp % 256 == 0 && !std::getenv("GML_B200_GRAD_FT128")) ? 256 : 128;   // feature-tile width
-            gp.Fp = p.Fp; gp.m_tiles = Nn_pad2 / 128; gp.f_tiles = p.Fp / ft; gp.nR = nr;
+            gp.Fp = p.Fp; gp.m_tiles = pad2 / 128; gp.f_tiles = p.Fp / ft; gp.nR = nr;
             gp.r_rows_per_limb = Nn_pad2; gp.block_stride = stride; gp.sample_blocks = ceil_div(h.Kp / 128, stride); gp.G = G64.p;
             gp.dbg = ep.dbg;
             const int tiles = gp.m_tiles * gp.f_tiles;
@@ -1382,10 +1437,10 @@ struct BackendTC : EvalBackend {
             span_end(st);
         }
         if (p.comm) {   // sample-sharded: exact int64 gradient sums and fp64 objective sums across the ranks
-            comm_allreduce_sum_f64(p.comm, fsum.p, Nn_pad1, st);
-            if (want_grad) comm_allreduce_sum_i64(p.comm, G64.p, (size_t)Nn_pad2 * p.Fp, st);
+            comm_allreduce_sum_f64(p.comm, fsum.p, pad1, st);
+            if (want_grad) comm_allreduce_sum_i64(p.comm, G64.p, (size_t)pad2 * p.Fp, st);
         }
-        tc_finalize_kernel<<<p.Nn, 128, 0, st>>>(p.form, p.Nn, p.Fp, fsum.p, G64.p, delta.p, f_out, g_out, want_grad ? 1 : 0);
+        tc_finalize_kernel<<<n_nodes, 128, 0, st>>>(p.form, p.Fp, fsum.p, G64.p, delta.p, f_out, g_out, want_grad ? 1 : 0, act_idx);
         GML_LAUNCHED();
     }
 };

@@ -30,7 +30,8 @@ struct FistaState {
     double *fY, *fYn, *L, *t, *tn, *q, *c, *gmap, *obj;
     double* best;     // smallest gradient-mapping norm seen
     int *stall, *streak;
-    int* status;      // 0 active, 1 converged, 2 stalled at the gradient noise floor
+    int* status;      // 0 active, 1 converged, 2 stalled at the gradient noise floor, 3 parked (done with the coarse level)
+    double park_tol;  // coarse level: a node whose gradient-mapping norm is below this waits for the fine level
     int* n_active;
     unsigned long long* gmax;   // bits of the largest gradient-mapping norm over the active nodes of this round
     int fine;                   // 1: the backend runs at its fine precision level
@@ -119,6 +120,12 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
         if (threadIdx.x == 0) s.status[u] = 1;
         return;
     }
+    // Coarse level: nothing retires, but a node that has reached the resolution of the coarse lattice stops taking
+    // part in the passes (its state is frozen at the last accepted point) until the fine level resumes it.
+    if (!s.fine && (gm <= s.park_tol || (s.lattice > 0.0 && gm <= 1.01 * s.L[u] * s.lattice))) {
+        if (threadIdx.x == 0) s.status[u] = 3;
+        return;
+    }
     const double fY = s.fY[u], fN = s.fYn[u];
     // Upper bound of the evaluation noise of f (fp32 per-sample terms): relative for the RISE/RPLE sums,
     // absolute for logRISE (f = log Z).  D is the slack of the descent test; for a locally quadratic f,
@@ -145,7 +152,8 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
     int stall = s.stall[u];
     double best = s.best[u];
     if (gm < 0.9 * best) { best = gm; stall = 0; } else ++stall;
-    const bool stalled = stall >= 200;       // the gradient mapping stopped improving: gradient noise floor
+    // the gradient mapping stopped improving: gradient noise floor (on the coarse level: its lattice; park after 12 rounds)
+    const bool stalled = stall >= (s.fine ? 200 : 12);
     for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
         s.X[o + f] = s.Z[o + f];
         s.Y[o + f] = s.Yn[o + f];
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
         streak = (c > 0.0 && D > 0.25 * c) ? streak + 1 : 0;
         if (streak >= 3) { s.L[u] *= 0.85; streak = 0; }
         s.streak[u] = streak;
-        if (stalled) s.status[u] = 2; else atomicAdd(s.n_active, 1);
+        if (stalled) s.status[u] = s.fine ? 2 : 3; else atomicAdd(s.n_active, 1);
     }
 }
 
@@ -171,6 +179,35 @@ __global__ void fista_init_kernel(FistaState s, double L0) {
     s.L[u] = L0 > 0.0 ? L0 : s.L[u] * -L0;      // first level: initial estimate; later levels: rescale by rho ratio
     s.t[u] = 1.0; s.status[u] = 0; s.gmap[u] = 1e300; s.obj[u] = 0.0;
     s.best[u] = 1e300; s.stall[u] = 0; s.streak[u] = 0;
+}
+
+// parked nodes rejoin (fine level): state kept, stall counters reset
+__global__ void fista_unpark_kernel(FistaState s) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= s.Nn) return;
+    if (s.status[u] == 3) { s.status[u] = 0; s.best[u] = 1e300; s.stall[u] = 0; }
+}
+
+// ordered list of the active nodes (single block; the host already knows the count)
+__global__ void __launch_bounds__(1024) fista_compact_kernel(FistaState s, int* __restrict__ idx) {
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int u0 = 0; u0 < s.Nn; u0 += 1024) {
+        const int u = u0 + threadIdx.x;
+        const bool on = u < s.Nn && s.status[u] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) warp_tot[w] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int i = 0; i < w; ++i) off += warp_tot[i];
+        if (on) idx[off + __popc(m & ((1u << lane) - 1))] = u;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += warp_tot[i]; base += t; }
+        __syncthreads();
+    }
 }
 
 // obj_u = f_u(X) + lambda |X_pen|_1
@@ -198,6 +235,8 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     DevBuf<double> Z, Y, Yn, G, Gn, fY, fYn, L, t, tn, q, c, gmap, best;
     DevBuf<int> status, n_active, stall, streak;
     DevBuf<unsigned long long> gmax;
+    DevBuf<int> act_idx;     // compacted list of the active nodes
+    act_idx.alloc(Nn);
     r.x.alloc(nx); r.objective.alloc(Nn);
     Z.alloc(nx); Y.alloc(nx); Yn.alloc(nx); G.alloc(nx); Gn.alloc(nx);
     fY.alloc(Nn); fYn.alloc(Nn); L.alloc(Nn); t.alloc(Nn); tn.alloc(Nn); q.alloc(Nn); c.alloc(Nn); gmap.alloc(Nn);
@@ -252,10 +291,9 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
         GML_LAUNCHED();
         rho_prev = rho;
         GML_CUDA(cudaMemcpyAsync(Y.p, r.x.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));   // warm start
-        // Precision levels: while the gradient mapping is far above the coarse lattice the passes run with a
-        // 3-limb iterate (lattice 2^-20) and one residual limb less; the last rounds run at full precision.
-        // Coarse-lattice points are fine-lattice points, so the switch needs no re-evaluation.
-        const double coarse_exit = 2e-4 * scale;
+        // Precision levels: every node first runs with a 3-limb iterate (lattice 2^-20) and one residual limb less until
+        // it reaches the tolerance or the resolution of that lattice, where it parks; when all have parked, the last
+        // rounds run at full precision.  Coarse-lattice points are fine-lattice points: the switch only refreshes (f, G).
         int level = (o.reserved[3] == 0 && user_tol <= 1e-4 && be->set_level(0, st)) ? 0 : 1;
         if (level == 1) be->set_level(1, st);
         auto sync_level = [&] {
@@ -263,7 +301,26 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
             s.eps_g = be->grad_noise() * scale;
         };
         sync_level();
-        be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += 1.0 / stride;
+        // Active-set compaction: once the active nodes fill at most 7/8 of the slots of the current pass, the passes are
+        // restricted to the active nodes (ordered list built on the device; the host knows the count from its per-round
+        // read).  Parked / converged nodes in the list stay as dead slots until the next compaction.
+        int cap = 0;                    // slots of the current passes (0: the backend evaluates the whole shard)
+        bool can_compact = o.reserved[6] == 0;
+        auto pass_units = [&] { return (cap ? (double)cap / Nn : 1.0) / stride; };
+        auto whole_shard = [&] { if (cap) { be->set_active(nullptr, 0, st); cap = 0; } };
+        auto maybe_compact = [&](int n_on) {
+            // worth it as soon as the padded slot count (128-node gradient tiles) shrinks by an eighth: the gather of the
+            // active nodes' spins costs a small fraction of one pass
+            const int64_t cur_pad = round_up(cap ? cap : Nn, 128), new_pad = round_up(n_on, 128);
+            const bool shrinks = new_pad * 8 <= cur_pad * 7 || (cur_pad == 128 && round_up(n_on, 64) < round_up(cap ? cap : Nn, 64));
+            if (!can_compact || n_on <= 0 || !shrinks) return;
+            fista_compact_kernel<<<1, 1024, 0, st>>>(s, act_idx.p);
+            GML_LAUNCHED();
+            if (be->set_active(act_idx.p, n_on, st)) cap = n_on; else can_compact = false;
+        };
+        s.park_tol = s.tol;
+        be->set_active(nullptr, 0, st);
+        be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += pass_units();
         active = Nn;
         for (; it < max_iter; ++it) {
             const bool trace = o.verbose > 2 && it == 5;     // one round dissected with events
@@ -274,7 +331,7 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
             fista_trial_kernel<<<Nn, 128, 0, st>>>(s);
             GML_LAUNCHED();
             if (trace) cudaEventRecord(ev[1], st);
-            be->eval(Yn.p, true, fYn.p, Gn.p, st); ++n_fg; fg_units += 1.0 / stride;
+            be->eval(Yn.p, true, fYn.p, Gn.p, st); ++n_fg; fg_units += pass_units();
             if (trace) cudaEventRecord(ev[2], st);
             GML_CUDA(cudaMemsetAsync(n_active.p, 0, sizeof(int), st));
             fista_accept_kernel<<<Nn, 128, 0, st>>>(s);
@@ -296,19 +353,29 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
             if (level == 0) {
                 const bool overflow = (h_flags & 2) != 0;           // some |x| reached 1: the 3-limb range is exhausted
                 if (overflow) be->note_coarse_overflow();
-                if (overflow || h_gmax <= coarse_exit || active == 0) {
+                // every node has parked (reached the tolerance or the resolution of the coarse lattice): the stragglers
+                // finish on the coarse level in compacted -- cheap -- passes instead of dragging all nodes to the fine one
+                if (overflow || active == 0) {
                     level = 1; be->set_level(1, st); sync_level();
-                    if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista: fine precision from round %d (gmap max %.3g%s)\n", it + 1, h_gmax, overflow ? ", coarse range overflow" : "");
-                    if (overflow || active == 0) {
+                    if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista: fine precision from round %d (gmap max %.3g, %d nodes still active%s)\n", it + 1, h_gmax, active, overflow ? ", coarse range overflow" : "");
+                    whole_shard();
+                    if (overflow) {
                         // restart from the last accepted iterate at full precision
                         fista_init_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s, -1.0);
                         GML_LAUNCHED();
                         GML_CUDA(cudaMemcpyAsync(Y.p, r.x.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
-                        active = Nn;
+                    } else {
+                        fista_unpark_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s);      // parked nodes rejoin with their state
+                        GML_LAUNCHED();
                     }
+                    active = Nn;
                     // the stored (f, G) at Y carry the coarse level's rounding noise: refresh them at full precision
-                    be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += 1.0 / stride;
+                    be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += pass_units();
+                } else {
+                    maybe_compact(active);
                 }
+            } else {
+                maybe_compact(active);
             }
             if (o.verbose > 1) {
                 std::vector<double> hg(Nn), hL(Nn);
@@ -325,7 +392,8 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     }
     s.lambda = prob.lambda;
     if (o.verbose > 0) { GML_CUDA(cudaStreamSynchronize(st)); t_loop = tick(); }
-    // objective at the returned point
+    // objective at the returned point (all nodes)
+    be->set_active(nullptr, 0, st);
     be->eval(r.x.p, false, fYn.p, nullptr, st); ++n_f;
     r.fg_units = fg_units; r.f_units = 1.0;
     fista_objective_kernel<<<Nn, 128, 0, st>>>(s, fYn.p);

@@ -115,6 +115,21 @@ def test_c2_node_shards_equal_full_solve(c2_session):
     assert np.abs(np.vstack(rows2) - full2).max() <= 1e-9
 
 
+def test_c2_active_set_compaction_changes_nothing(c2_session):
+    """The passes drop parked / converged nodes (compacted slot list, gathered spin tiles).  Node problems are
+    independent and the contractions exact, so at one precision level the compacted solve returns the rows of the
+    uncompacted one; with the coarse level the paths differ only in when nodes park (solver tolerance)."""
+    sess, _, _ = c2_session
+    a, ia = sess.solve_pairwise(RISE(0.4, False), B200(coarse_level=False, compaction=True), return_info=True)
+    b, ib = sess.solve_pairwise(RISE(0.4, False), B200(coarse_level=False, compaction=False), return_info=True)
+    assert ia["n_unconverged"] == 0 and ib["n_unconverged"] == 0
+    assert np.abs(a - b).max() <= 1e-9
+    assert ia["evals"] < 0.9 * ib["evals"]          # the compacted passes did less work
+    c = sess.solve_pairwise(RISE(0.4, False), B200(compaction=True))
+    d = sess.solve_pairwise(RISE(0.4, False), B200(compaction=False))
+    assert np.abs(c - d).max() <= 5e-6 and np.abs(c - a).max() <= 5e-6
+
+
 def test_device_histogram_builder_and_sampler():
     """raw Gibbs samples (N=16, M=1e6) -> device dedup -> learn; the device histogram equals the
     host np.unique histogram, and learn() on it recovers the generating model (test/runtests.jl:105-127 style)."""
