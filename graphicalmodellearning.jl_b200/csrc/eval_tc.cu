@@ -211,7 +211,10 @@ constexpr int NODE_TILE2 = 128;                  // nodes per gradient tile (M =
 // residual grid: |q| <= r_qmax(nR), stored as q + r_bias(nR) in nR unsigned bytes (nR <= 3 round with the
 // magic-number trick, which needs |q| < 2^22)
 __host__ __device__ constexpr int r_qmax(int nR) { return nR == 2 ? 32000 : (nR == 3 ? 4000000 : 1000000000); }
-__host__ __device__ constexpr unsigned r_bias(int nR) { return nR == 2 ? 0x8000u : (nR == 3 ? 0x800000u : 0x80000000u); }
+// The biases of nR <= 3 are the ones the rounding constant provides for free: float_as_int(q + 1.5 * 2^23 [+ 2^15])
+// holds q + 2^22 [+ 2^15] in its mantissa bits, so the stored bytes are plain byte extracts of that word.
+__host__ __device__ constexpr unsigned r_bias(int nR) { return nR == 2 ? 0x8000u : (nR == 3 ? 0x400000u : 0x80000000u); }
+__host__ __device__ constexpr float r_magic(int nR) { return nR == 2 ? 12582912.f + 32768.f : 12582912.f; }
 
 __device__ __forceinline__ int balanced_digit(int& q) {   // returns q mod 128 in [-64, 63], q <- (q - d) / 128
     const int d = ((q + 64) & 127) - 64;
@@ -273,6 +276,7 @@ struct EnergyParams {
     float lattice;                         // value of one unit of the combined integer energy
     const float* w32;
     uint8_t* R;                            // residual digit planes [SB][nR][Nn_pad2][128]
+    uint8_t* r_scratch;                    // [4][64][128] sink for the stores of a duplicated tail block
     const float* inv_dr;                   // [Nn_pad1] 1/deltaR
     double* fsum;                          // [Nn_pad1] objective sums
     int dbg;                               // ablation switches (only in -DGML_TC_ABLATE builds; see GML_DBG)
@@ -318,6 +322,12 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
     return v;
 }
 
+// a ^ (b & c) in one LOP3: flips the sign of float a when the spin byte shifted to the top of b is negative
+__device__ __forceinline__ float flip_sign(float a, uint32_t b) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, 0x80000000, 0x78;" : "=r"(d) : "r"(__float_as_uint(a)), "r"(b));
+    return __uint_as_float(d);
+}
 __device__ __forceinline__ float fast_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -385,10 +395,10 @@ __device__ __forceinline__ void energy_epilogue_math(const EnergyParams& p, uint
             if (GRAD) {
                 // r = s_u * gterm in units of the node's residual grid, rounded to nearest, plus the
                 // bias that makes all balanced digits non-negative
-                const float vq = __uint_as_float(__float_as_uint(gterm * lds_f32(scale_addr + 4 * nit)) ^ sgn);
-                unsigned qb;
-                if (NR == 4) qb = (unsigned)__float2int_rn(vq) + R_BIAS;
-                else qb = (unsigned)__float_as_int(vq + 12582912.f) - 0x4B400000u + R_BIAS;      // |vq| < 2^22
+                const float sscale = __uint_as_float(__float_as_uint(lds_f32(scale_addr + 4 * nit)) ^ sgn);      // s_u / deltaR
+                unsigned qb;      // low NR bytes = q + BIAS
+                if (NR == 4) qb = (unsigned)__float2int_rn(gterm * sscale) + R_BIAS;
+                else qb = (unsigned)__float_as_int(fmaf(gterm, sscale, r_magic(NR)));      // round to nearest, |q| < 2^22; bias from the constant
                 uint8_t* dst = rg + nit * 128;
 #pragma unroll
                 for (int j = 0; j < NR; ++j)      // plane 0 = most significant byte
@@ -582,18 +592,19 @@ __global__ void __launch_bounds__(E_THREADS, 1) tc_energy_kernel(const __grid_co
 // are already in registers (a[limb][node]); sw0 / sw1 = the 8 spin bytes.  Same arithmetic as above.
 template <int FORM, bool GRAD, int XL, int NR>
 __device__ __forceinline__ void energy_chunk_math(const EnergyParams& p, int32_t (&a)[4][8], uint32_t sw0, uint32_t sw1, uint32_t scale_addr,
-                                                  uint8_t* __restrict__ rg, int64_t limb_stride, float wk, float* __restrict__ facc, bool store) {
+                                                  uint8_t* const (&rgp)[4] /* per digit plane: address of this thread's byte of node 0 */,
+                                                  int node0, float wk, float* __restrict__ facc) {
     const float c_arg = -p.lattice * 1.4426950408889634f;
     constexpr unsigned R_BIAS = r_bias(NR);
     if (GML_DBG(p, 32)) { facc[0] += __int_as_float(a[0][0] ^ a[1][3] ^ a[2][7] ^ (XL == 4 ? a[3][5] : 0)); return; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const uint32_t w = i < 4 ? sw0 : sw1;
-        const uint32_t sgn = ((i & 3) == 3 ? w : (w << (24 - 8 * (i & 3)))) & 0x80000000u;
+        const uint32_t sb_top = (i & 3) == 3 ? w : (w << (24 - 8 * (i & 3)));      // spin byte (0x01 / 0xFF / 0x00) in the top byte
         float e;
         if (XL == 3) e = __int2float_rn((a[0][i] * 128 + a[1][i]) * 128 + a[2][i]);
         else e = fmaf(__int2float_rn(a[0][i] * 128 + a[1][i]), 16384.f, __int2float_rn(a[2][i] * 128 + a[3][i]));
-        const float es = __uint_as_float(__float_as_uint(e) ^ sgn);
+        const float es = flip_sign(e, sb_top);
         float fterm, gterm;
         if (FORM == GML_B200_RPLE) {
             const float t2 = -2.f * p.lattice * es;
@@ -601,19 +612,20 @@ __device__ __forceinline__ void energy_chunk_math(const EnergyParams& p, int32_t
             fterm = wk * fmaf(fast_lg2(1.f + ex), 0.6931471805599453f, fmaxf(t2, 0.f));
             gterm = __fdividef(2.f * wk * (t2 > 0.f ? 1.f : ex), 1.f + ex);
         } else {
-            fterm = wk * fast_ex2(fminf(es * c_arg, 115.f));
+            // no clamp: |t| <= |x_u|_1 keeps the argument in range; an overflow for a wild trial point (|x_u|_1 > 80) gives
+            // f = inf, which the driver's descent test rejects
+            fterm = wk * fast_ex2(es * c_arg);
             gterm = fterm;
         }
         facc[i] += fterm;
         if (GRAD) {
-            const float vq = __uint_as_float(__float_as_uint(gterm * lds_f32(scale_addr + 4 * i)) ^ sgn);
-            unsigned qb;
-            if (NR == 4) qb = (unsigned)__float2int_rn(vq) + R_BIAS;
-            else qb = (unsigned)__float_as_int(vq + 12582912.f) - 0x4B400000u + R_BIAS;
-            uint8_t* dst = rg + i * 128;
-            if (store && !GML_DBG(p, 64)) {
+            const float sscale = flip_sign(lds_f32(scale_addr + 4 * i), sb_top);      // s_u / deltaR
+            unsigned qb;      // low NR bytes = q + BIAS
+            if (NR == 4) qb = (unsigned)__float2int_rn(gterm * sscale) + R_BIAS;
+            else qb = (unsigned)__float_as_int(fmaf(gterm, sscale, r_magic(NR)));   // round to nearest, |q| < 2^22; bias from the constant
+            if (!GML_DBG(p, 64)) {
 #pragma unroll
-                for (int j = 0; j < NR; ++j) dst[j * limb_stride] = (uint8_t)(qb >> (8 * (NR - 1 - j)));
+                for (int j = 0; j < NR; ++j) rgp[j][(node0 + i) * 128] = (uint8_t)(qb >> (8 * (NR - 1 - j)));      // plane 0 = most significant byte
             }
         }
     }
@@ -881,7 +893,12 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
                 ++since_flush;
                 const float wk = valid ? wk_next : 0.f;
                 if (pb + 1 < b1) wk_next = __ldg(p.w32 + block_of(pb + 1) * 128 + row);
-                uint8_t* rg = p.R + ((sb * NR * p.r_rows_per_limb + nt * NODE_TILE1 + half * NPT) * 128 + row);
+                // digit planes of this thread's first node; the duplicate block of an odd tail writes to a scratch tile instead
+                uint8_t* rgp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    rgp[j] = valid ? p.R + (((sb * NR + j) * p.r_rows_per_limb + nt * NODE_TILE1 + half * NPT) * 128 + row)
+                                   : p.r_scratch + ((j * NODE_TILE1 + half * NPT) * 128 + row);
                 const uint32_t spin_base = smem_u32(s_spin) + slot * E_S_BYTES;
                 uint32_t sw[4];
                 if (p.spin_vec) {
@@ -896,7 +913,7 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
                 // ---- nodes 0..7 (in ra); nodes 8..15 start loading
                 epi_wait<XL>(ra);
                 epi_issue<XL>(tlane + as * 256 + 8, rb);
-                energy_chunk_math<FORM, GRAD, XL, NR>(p, ra, sw[0], sw[1], scale_addr, rg, limb_stride, wk, facc, valid);
+                energy_chunk_math<FORM, GRAD, XL, NR>(p, ra, sw[0], sw[1], scale_addr, rgp, 0, wk, facc);
                 // ---- nodes 8..15 (in rb): the accumulator is now fully read
                 epi_wait<XL>(rb);
                 tc_fence_before();
@@ -909,7 +926,7 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
                     pre = __all_sync(0xffffffffu, mbar_test(&tfull[as_n], aphase_n) && mbar_test(&sfull[slot_n], sphase_n));
                     if (pre) { tc_fence_after(); epi_issue<XL>(tlane + as_n * 256, ra); }
                 }
-                energy_chunk_math<FORM, GRAD, XL, NR>(p, rb, sw[2], sw[3], scale_addr + 32, rg + 8 * 128, limb_stride, wk, facc + 8, valid);
+                energy_chunk_math<FORM, GRAD, XL, NR>(p, rb, sw[2], sw[3], scale_addr + 32, rgp, 8, wk, facc + 8);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sempty[slot]);
                 as = as_n; aphase = aphase_n; slot = slot_n; sphase = sphase_n;
@@ -1195,6 +1212,7 @@ struct BackendTC : EvalBackend {
     DevBuf<long long> colsum;           // [Fp] column sums of the feature matrix over the blocks of the current stride
     int64_t colsum_stride = 0;          // stride colsum was computed for (0 = not yet)
     DevBuf<int> flags;
+    DevBuf<uint8_t> r_scratch;
     // active-set compaction (set_active): slot -> node list, spins of the listed nodes, their TMA map
     const int* act_idx = nullptr;
     int n_act = 0;
@@ -1228,6 +1246,7 @@ struct BackendTC : EvalBackend {
         G64.alloc((size_t)Nn_pad2 * p.Fp);
         colsum.alloc(p.Fp);
         flags.alloc(1);
+        r_scratch.alloc(4 * NODE_TILE1 * 128);
         GML_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int), st));
         // rows of R that belong to padding nodes are never written by GEMM-1 tiles beyond Nn_pad1: clear once
         GML_CUDA(cudaMemsetAsync(R.p, 0, (size_t)nR * Nn_pad2 * h.Kp, st));
@@ -1377,7 +1396,7 @@ struct BackendTC : EvalBackend {
         EnergyParams ep{};
         ep.Kp = h.Kp; ep.Fp = p.Fp; ep.Fspin = Fspin; ep.Nn = n_nodes; ep.n_tiles = pad1 / NODE_TILE1;
         ep.block_stride = stride; ep.sample_blocks = ceil_div(h.Kp / 128, stride); ep.r_rows_per_limb = Nn_pad2; ep.nR = nr; ep.form = p.form; ep.lattice = (float)lattice();
-        ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p; ep.R = reinterpret_cast<uint8_t*>(R.p);
+        ep.w32 = h.w32.p; ep.inv_dr = inv_dr.p; ep.fsum = fsum.p; ep.R = reinterpret_cast<uint8_t*>(R.p); ep.r_scratch = r_scratch.p;
         ep.node_begin_row = act_idx ? 0 : first_row; ep.spin_vec = (act_idx || spin_vec) ? 1 : 0;
         const CUtensorMap& tmSvUse = act_idx ? tmSvAct : tmSv;
         const char* dbg_env = std::getenv("GML_B200_DBG");
