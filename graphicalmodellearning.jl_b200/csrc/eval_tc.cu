@@ -16,12 +16,16 @@
 //     start at -BIAS * colsum[f]); partial tiles are combined with int64 atomics, so the result is
 //     independent of the reduction order (bitwise reproducible).
 //   * two precision levels (set_level): the fine level above, and a coarse level (lattice 2^-20,
-//     3 iterate limbs, |x| < 1, one residual limb fewer) used by the FISTA driver far from the
-//     optimum; nodes never retire on the coarse level and (f, G) are refreshed on the switch.
+//     3 iterate limbs, |x| < 1, one residual digit fewer) on which every node runs until it reaches the
+//     resolution of that lattice; nodes never retire on the coarse level and (f, G) are refreshed on the switch.
+//   * active-set compaction (set_active): the passes can be restricted to a list of nodes (slot -> node
+//     indirection in the quantiser / finaliser, spins of the listed nodes gathered into P_act).
 //
 // Warp roles: warp 0 issues TMA, warp 1 issues tcgen05.mma, the remaining warps (16 in the energy
-// kernel, 4 in the gradient kernel) run the TMEM epilogues; the energy kernel double-buffers its
-// 2 x 256 TMEM columns so the MMA of sample block b+1 overlaps the epilogue of block b.
+// kernels, 4 in the gradient kernel) run the TMEM epilogues; the energy kernels double-buffer their
+// 2 x 256 TMEM columns so the MMA of sample block b+1 overlaps the epilogue of block b.  The energy GEMM
+// runs on CTA pairs (tc_energy_pair_kernel: cta_group::2, the limb tile resident in shared memory) whenever
+// a half limb tile fits (Fp <= 1024); tc_energy_kernel is the single-CTA form that streams the limb tile.
 //
 // Replaces the per-node JuMP expression evaluation of src/GraphicalModelLearning.jl:162-172 (and
 // :271-281, :309-319, :106-119) for all nodes at once.

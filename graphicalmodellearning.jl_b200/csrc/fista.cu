@@ -10,6 +10,11 @@
 //              which must hold for any pair of points once L bounds the curvature.  Passed: X <- Z,
 //              (Y, G, f) <- (Y', G', f').  Failed: L_u *= 2 and the node retries from the same (Y, G).
 //
+// Nodes drop out of the passes as they finish: on the coarse precision level of a lattice backend a node that has
+// reached the tolerance or the resolution of the coarse lattice parks (status 3) until all have, on the fine level a
+// converged node retires (status 1); the passes are then restricted to an ordered list of the active nodes
+// (fista_compact_kernel -> EvalBackend::set_active), so late rounds cost what their active nodes cost.
+//
 // Testing the lemma at Y' instead of at Z saves the separate objective-only pass of textbook
 // backtracking FISTA; it probes the curvature along the direction the iterate actually moves.
 // The problem solved per node is the reference's (src/GraphicalModelLearning.jl:169-177 etc.) with
