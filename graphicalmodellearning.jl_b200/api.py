@@ -86,6 +86,7 @@ class B200(GMLMethod):
     coarse_level: bool = True     # fista_tc: 3-limb iterate / one residual limb less while far from convergence
     devices: int = 1              # one-shot learn(): shard the nodes over this many GPUs from this process
     compaction: bool = True       # FISTA: restrict the passes to the nodes that are still active (parked / converged ones drop out)
+    warm_start: bool = False      # FISTA, full pairwise solves: start from the mean-field couplings (experimental, opt-in)
     last_stats: dict = field(default_factory=dict, repr=False, compare=False)
 
     def _opts(self, node_begin: int = 0, node_end: int = 0, stream: int = 0) -> _lib.Opts:
@@ -104,6 +105,7 @@ class B200(GMLMethod):
         o.reserved[3] = 0 if self.coarse_level else 1
         o.reserved[4] = int(self.devices)
         o.reserved[6] = 0 if self.compaction else 1
+        o.reserved[7] = 1 if self.warm_start else 0
         return o
 
 

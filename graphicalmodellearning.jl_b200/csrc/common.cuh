@@ -147,6 +147,9 @@ void solve_newton(const NodeProblem& p, const gml_b200_opts& o, SolveResult& r, 
 // --- fista.cu : batched FISTA driver over an evaluation backend
 void solve_fista(const NodeProblem& p, const gml_b200_opts& o, int backend, SolveResult& r, cudaStream_t st);
 
+// --- warmstart.cu : mean-field starting point of a full pairwise solve from its first-pass gradient (opt-in)
+bool meanfield_start(const double* G0, int N, int Fp, const uint8_t* pen, double xmax, double lattice, double* x0, cudaStream_t st);
+
 // --- evaluation backends (objective / gradient passes over the histogram)
 struct EvalBackend {
     virtual ~EvalBackend() {}

@@ -62,7 +62,8 @@ typedef struct gml_b200_opts {
                             reserved[4] > 1: gml_b200_learn_pairwise shards the nodes over that many devices
                             (device, device+1, ...) from this one process, one host thread per device;
                             reserved[5] == 1: gml_b200_bench_passes times the coarse precision level;
-                            reserved[6] != 0: disable the active-set compaction of the FISTA passes */
+                            reserved[6] != 0: disable the active-set compaction of the FISTA passes;
+                            reserved[7] != 0: (experimental) mean-field warm start of cold full pairwise FISTA solves */
 } gml_b200_opts;
 
 typedef struct gml_b200_stats {
