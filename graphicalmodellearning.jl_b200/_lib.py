@@ -23,7 +23,7 @@ EXPORTS = (
     "gml_b200_attach_histogram_device", "gml_b200_num_samples", "gml_b200_solve_pairwise",
     "gml_b200_solve_pairwise_device", "gml_b200_solve_pairwise_path", "gml_b200_solve_multibody", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
     "gml_b200_symmetrize_device",
-    "gml_b200_sample_gibbs_device", "gml_b200_build_histogram_device",
+    "gml_b200_sample_gibbs_device", "gml_b200_sample_gibbs_terms_device", "gml_b200_build_histogram_device",
     "gml_b200_comm_unique_id", "gml_b200_comm_init", "gml_b200_comm_globalize_histogram",
 )
 
@@ -38,7 +38,7 @@ class Opts(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("solver_used", ctypes.c_int32), ("iterations", ctypes.c_int32),
                 ("n_fg_passes", ctypes.c_int32), ("n_f_passes", ctypes.c_int32),
-                ("n_unconverged", ctypes.c_int32), ("reserved_i", ctypes.c_int32),
+                ("n_unconverged", ctypes.c_int32), ("n_stalled", ctypes.c_int32),
                 ("kernel_launches", ctypes.c_int64), ("evals", ctypes.c_double),
                 ("pack_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("solve_ms", ctypes.c_double),
                 ("d2h_ms", ctypes.c_double), ("total_ms", ctypes.c_double),
@@ -101,6 +101,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gml_b200_symmetrize_device.argtypes = [vp, c.c_int32, vp]
     lib.gml_b200_sample_gibbs_device.argtypes = [c.c_int32, c.c_int32, vp, vp, vp, vp, c.c_int64, c.c_int32,
                                                  c.c_uint64, vp, c.c_int64, vp]
+    lib.gml_b200_sample_gibbs_terms_device.argtypes = [c.c_int32, c.c_int32, c.c_int32, c.c_int32, vp, vp, c.c_int64, c.c_int32,
+                                                       c.c_uint64, vp, c.c_int64, vp]
     lib.gml_b200_build_histogram_device.argtypes = [c.c_int32, vp, c.c_int64, c.c_int32, c.c_int64, vp, c.c_int64, vp,
                                                     c.POINTER(c.c_int64), vp]
     lib.gml_b200_comm_unique_id.argtypes = [vp]

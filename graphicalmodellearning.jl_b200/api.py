@@ -278,6 +278,28 @@ def learn(samples, formulation: Optional[GMLFormulation] = None, method: Optiona
     return learn_packed(counts, spins, formulation, method, return_info=return_info)
 
 
+def sample_terms_device(terms: Dict[Tuple[int, ...], float], num_spins: int, n_samples: int, sweeps: int = 60,
+                        seed: int = 0, device: int = 0):
+    """Device multi-chain Gibbs sampler (csrc/sampler.cu) for a +-1 model given as a FactorGraph-style term dict
+    {(i, ...): weight} with 1-based spin labels (keys of length 1 are fields) -- the distribution the reference's
+    `sample` draws from by enumerating all 2^N configurations (src/sampling.jl:58-88), which stops at N ~ 25.
+    One sample per chain after `sweeps` sweeps from a random start.  Returns a torch int8 tensor [N x n_samples]
+    (spin-major, the layout the solver uploads) on `device`."""
+    import torch
+    lib = _lib.load()
+    order = max((len(k) for k in terms), default=1)
+    idx = -np.ones((max(len(terms), 1), order), dtype=np.int32)
+    wts = np.zeros(max(len(terms), 1), dtype=np.float32)
+    for t, (k, v) in enumerate(terms.items()):
+        idx[t, :len(k)] = np.asarray(k, dtype=np.int32) - 1
+        wts[t] = v
+    out = torch.empty((num_spins, n_samples), dtype=torch.int8, device=f"cuda:{device}")
+    _lib.check(lib.gml_b200_sample_gibbs_terms_device(device, num_spins, order, len(terms), _ptr(idx), _ptr(wts),
+                                                      n_samples, sweeps, seed, ctypes.c_void_p(out.data_ptr()),
+                                                      n_samples, None))
+    return out
+
+
 class Session:
     """Handle API (include/gml_b200.h): keeps the histogram resident in HBM across calls."""
 
@@ -346,14 +368,33 @@ class Session:
         _lib.check(rc)
         return method.last_stats
 
-    def eval_pairwise(self, formulation, x: np.ndarray, backend: str = "fista_tc", want_grad: bool = True):
-        """f_u and grad f_u at rows x [N x (N+1)] (couplings then field)."""
+    def solve_multibody(self, formulation, method: B200, lam: Optional[float] = None, return_info=False):
+        """multiRISE on the resident histogram: the raw per-node values [N x n_keys] in the reference's key order
+        (src/GraphicalModelLearning.jl:94-104); Dict assembly / mean-symmetrisation: learn_packed."""
+        N = self.N
+        order = int(formulation.interaction_order)
+        if lam is None:
+            lam = regularizer_lambda(formulation.regularizer, N, self.num_samples)
+        n_keys = int(self._lib.gml_b200_multibody_num_keys(N, order))
+        vals, obj = np.zeros((N, n_keys)), np.zeros(N)
+        st = _lib.Stats()
+        opts = method._opts()
+        rc = self._lib.gml_b200_solve_multibody(self._h, order, lam, ctypes.byref(opts), _ptr(vals), _ptr(obj), ctypes.byref(st))
+        method.last_stats = st.as_dict()
+        _lib.check(rc)
+        return (vals, {"lambda": lam, "objective": obj, **method.last_stats}) if return_info else vals
+
+    def eval_pairwise(self, formulation, x: np.ndarray, backend: str = "fista_tc", want_grad: bool = True,
+                      coarse: bool = False):
+        """f_u and grad f_u at rows x [N x (N+1)] (couplings then field).  coarse=True evaluates on the tensor-core
+        backend's coarse precision level (iterate lattice 2^-20, |x| < 1, 16-bit residual digits)."""
         form_id = {RISE: 0, logRISE: 1, RPLE: 2}[type(formulation)]
         x = np.ascontiguousarray(x, dtype=np.float64)
         assert x.shape == (self.N, self.N + 1)
         f = np.zeros(self.N)
         g = np.zeros_like(x) if want_grad else None
         opts = B200(solver=backend)._opts()
+        opts.reserved[5] = 1 if coarse else 0
         _lib.check(self._lib.gml_b200_eval_pairwise(self._h, form_id, ctypes.byref(opts), _ptr(x), _ptr(f),
                                                     _ptr(g) if want_grad else None))
         return f, g

@@ -162,6 +162,7 @@ void finish_stats(gml_b200_stats* stats, const SolveResult& r, int solver_used, 
     stats->n_fg_passes = r.n_fg;
     stats->n_f_passes = r.n_f;
     stats->n_unconverged = r.n_unconverged;
+    stats->n_stalled = r.n_stalled;
     stats->kernel_launches = g_launches;
     const double fg = r.fg_units >= 0.0 ? r.fg_units : r.n_fg, fo = r.f_units >= 0.0 ? r.f_units : r.n_f;
     stats->evals = (double)Nn * (double)K * (fg + 0.5 * fo);
@@ -184,7 +185,7 @@ void solve_pairwise_rows_one(gml_b200_handle* h, int formulation, double lambda,
     NodeProblem p;
     p.hist = &hist; p.Q = hist.base.p; p.F = N + 1; p.Fp = hist.Fb;
     p.form = formulation; p.lambda = lambda; p.Nn = ne - nb;
-    if (o.reserved[2] != 0) {
+    if (o.reserved[2] == 1) {
         GML_REQUIRE(h->comm != nullptr, "sample-sharded solve needs gml_b200_comm_init first");
         GML_REQUIRE(hist.M_local > 0.0, "sample-sharded solve needs gml_b200_comm_globalize_histogram after the upload");
         GML_REQUIRE(o.solver == GML_B200_SOLVER_FISTA_TC || (o.solver == GML_B200_SOLVER_AUTO && p.F > NEWTON_MAX_F),
@@ -227,7 +228,7 @@ void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, con
     const int F = N + 1;
     int solver = o.solver == GML_B200_SOLVER_AUTO ? (F <= NEWTON_MAX_F ? GML_B200_SOLVER_NEWTON : GML_B200_SOLVER_FISTA_TC) : o.solver;
     int chunk = ne - nb;
-    if (solver == GML_B200_SOLVER_FISTA_TC && !warm && o.reserved[2] == 0) {
+    if (solver == GML_B200_SOLVER_FISTA_TC && !warm && o.reserved[2] != 1) {
         size_t free_b = 0, total_b = 0;
         GML_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const double Kp = (double)hist.Kp, Fp = (double)hist.Fb;
@@ -260,6 +261,7 @@ void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, con
             if (err.code != GML_B200_ENOTCONV) throw;
         }
         unconverged += cur.n_unconverged;
+        acc.n_stalled += cur.n_stalled;
         acc.solver_used = cur.solver_used;
         acc.iterations = std::max(acc.iterations, cur.iterations);
         acc.n_fg_passes += cur.n_fg_passes; acc.n_f_passes += cur.n_f_passes;
@@ -605,11 +607,16 @@ int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b2
         pairwise_setup_kernel<<<p.Nn, 128, 0, st>>>(N, p.Fp, nb, p.Nn, p.spin_row.p, p.pen.p);
         GML_LAUNCHED();
         std::unique_ptr<EvalBackend> be(o.solver == GML_B200_SOLVER_FISTA_TC ? make_backend_tc(p, st) : make_backend_cc(p, st));
+        if (o.reserved[5] == 1)      // evaluate on the coarse precision level (lattice 2^-20, |x| < 1)
+            GML_REQUIRE(be->set_level(0, st), "this backend has no coarse precision level");
         std::vector<double> hx((size_t)p.Nn * p.Fp, 0.0);
-        const double lat = be->lattice();
+        const double lat = be->lattice(), xmax = be->x_range();
         for (int u = 0; u < p.Nn; ++u)
             for (int f = 0; f < F; ++f) {
                 double v = (f == nb + u) ? 0.0 : x[(size_t)u * F + f];
+                GML_REQUIRE(std::isfinite(v) && (xmax <= 0.0 || std::fabs(v) <= xmax),
+                            "eval: a coefficient lies outside the fixed-point range of the tensor-core backend "
+                            "(|x| < 7.9 on the fine level, < 0.99 on the coarse one); use solver = FISTA_CC");
                 if (lat > 0.0) v = std::nearbyint(v / lat) * lat;
                 hx[(size_t)u * p.Fp + f] = v;
             }
@@ -723,12 +730,20 @@ static int learn_pairwise_multi_device(const double* counts, const int8_t* spins
     int rc = GML_B200_OK;
     for (int r = 0; r < n_dev; ++r)
         if (rcs[r] != GML_B200_OK && (rc == GML_B200_OK || rc == GML_B200_ENOTCONV)) { rc = rcs[r]; set_error("device " + std::to_string(base.device + r) + ": " + errs[r]); }
-    if (symmetrize && (rc == GML_B200_OK || rc == GML_B200_ENOTCONV))
-        for (int i = 0; i < N; ++i)
-            for (int j = i + 1; j < N; ++j) {
-                const double v = 0.5 * (out_theta[(size_t)i + (size_t)N * j] + out_theta[(size_t)j + (size_t)N * i]);   // (:185)
-                out_theta[(size_t)i + (size_t)N * j] = v; out_theta[(size_t)j + (size_t)N * i] = v;
-            }
+    if (symmetrize && (rc == GML_B200_OK || rc == GML_B200_ENOTCONV)) {
+        // 0.5 (R + R') (:185) on the first device: the rows of all shards are already in the caller's matrix
+        const int rs = guarded([&] {
+            GML_CUDA(cudaSetDevice(base.device));
+            DevBuf<double> m;
+            m.alloc((size_t)N * N);
+            GML_CUDA(cudaMemcpy(m.p, out_theta, sizeof(double) * N * N, cudaMemcpyHostToDevice));
+            dim3 b(32, 8), g((unsigned)ceil_div(N, 32), (unsigned)ceil_div(N, 8));
+            symmetrize_kernel<<<g, b>>>(m.p, N);       // symmetric in (i, j): the column-major matrix is symmetrised in place
+            GML_LAUNCHED();
+            GML_CUDA(cudaMemcpy(out_theta, m.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost));
+        });
+        if (rs != GML_B200_OK) rc = rs;
+    }
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         for (int r = 0; r < n_dev; ++r) {
@@ -749,11 +764,89 @@ static int learn_pairwise_multi_device(const double* counts, const int8_t* spins
     return rc;
 }
 
+// Single-process multi-GPU, sample-sharded form: one host thread per device, each uploads ITS slice of the histogram
+// rows (one pass over the host link per byte, no replication), the threads join one NCCL communicator and advance all
+// node problems in lockstep (all-reduce of the exact int64 gradient sums per pass, csrc/comm.cu).  Every device ends
+// with the full solution; device `base.device` symmetrises it on the device (:184-186) and writes the caller's matrix.
+static int learn_pairwise_multi_device_samples(const double* counts, const int8_t* spins, int64_t K, int32_t N, int64_t ld,
+                                               int32_t formulation, double lambda, int32_t symmetrize, const gml_b200_opts& base,
+                                               int n_dev, double* out_theta, double* out_objective, gml_b200_stats* stats) {
+    const double t0 = now_ms();
+    uint8_t ident[128];
+    if (gml_b200_comm_unique_id(ident) != GML_B200_OK) return -1;      // no NCCL: the caller falls back to node shards
+    std::vector<int> rcs(n_dev, GML_B200_OK);
+    std::vector<std::string> errs(n_dev);
+    std::vector<gml_b200_stats> sts(n_dev);
+    std::vector<std::thread> threads;
+    const int64_t per = round_up(ceil_div(K, n_dev), 256);
+    for (int r = 0; r < n_dev; ++r)
+        threads.emplace_back([&, r] {
+            gml_b200_handle* h = nullptr;
+            gml_b200_opts o = base;
+            o.device = base.device + r; o.stream = nullptr;
+            o.node_begin = 0; o.node_end = 0; o.reserved[2] = 1; o.reserved[4] = 0;
+            o.solver = GML_B200_SOLVER_FISTA_TC;
+            const int64_t k0 = std::min<int64_t>(K, r * per), k1 = std::min<int64_t>(K, (r + 1) * per);
+            std::memset(&sts[r], 0, sizeof(gml_b200_stats));
+            gml_b200_stats up{};
+            int rc = gml_b200_create(&h, o.device);
+            if (rc == GML_B200_OK) rc = gml_b200_upload_histogram(h, counts + k0, spins + k0, k1 - k0, N, ld, &up);
+            // every thread must reach the communicator set-up, also after a failed upload (the others would wait for ever)
+            const int rc_comm = h ? gml_b200_comm_init(h, ident, r, n_dev) : GML_B200_ECUDA;
+            if (rc == GML_B200_OK) rc = rc_comm;
+            if (rc_comm == GML_B200_OK) {       // leave together if any device failed so far
+                int agreed = rc;
+                if (guarded([&] { agreed = comm_agree_max(h->comm, rc, h->own_stream); }) == GML_B200_OK && agreed != GML_B200_OK && rc == GML_B200_OK) {
+                    rc = agreed; set_error("another device of the multi-device solve failed");
+                }
+            }
+            if (rc == GML_B200_OK) rc = gml_b200_comm_globalize_histogram(h);
+            if (rc == GML_B200_OK) {
+                if (r == 0) rc = gml_b200_solve_pairwise(h, formulation, lambda, symmetrize, &o, out_theta, out_objective, &sts[r]);
+                else {
+                    DevBuf<double> rows;
+                    try { rows.alloc((size_t)N * N); } catch (const CudaError& e) { rc = e.code; }
+                    if (rc == GML_B200_OK) rc = gml_b200_solve_pairwise_device(h, formulation, lambda, &o, rows.p, nullptr, &sts[r]);
+                    cudaStreamSynchronize(h->own_stream);
+                }
+                sts[r].pack_ms = up.pack_ms; sts[r].h2d_ms = up.h2d_ms; sts[r].kernel_launches += up.kernel_launches;
+            }
+            if (rc != GML_B200_OK) errs[r] = gml_b200_last_error();
+            rcs[r] = rc;
+            gml_b200_destroy(h);
+        });
+    for (auto& t : threads) t.join();
+    int rc = GML_B200_OK;
+    for (int r = 0; r < n_dev; ++r)
+        if (rcs[r] != GML_B200_OK && (rc == GML_B200_OK || rc == GML_B200_ENOTCONV)) { rc = rcs[r]; set_error("device " + std::to_string(base.device + r) + ": " + errs[r]); }
+    if (stats) {
+        *stats = sts[0];
+        for (int r = 1; r < n_dev; ++r) {
+            stats->kernel_launches += sts[r].kernel_launches;
+            stats->evals += sts[r].evals;
+            stats->solve_ms = std::max(stats->solve_ms, sts[r].solve_ms);
+            stats->h2d_ms = std::max(stats->h2d_ms, sts[r].h2d_ms);
+            stats->pack_ms = std::max(stats->pack_ms, sts[r].pack_ms);
+        }
+        stats->total_ms = now_ms() - t0;
+    }
+    return rc;
+}
+
 int gml_b200_learn_pairwise(const double* counts, const int8_t* spins, int64_t K, int32_t N, int64_t ld,
                             int32_t formulation, double lambda, int32_t symmetrize, const gml_b200_opts* opts,
                             double* out_theta, double* out_objective, gml_b200_stats* stats) {
     if (opts && opts->reserved[4] > 1) {
         const int n_dev = std::min<int>(opts->reserved[4], std::max(1, gml_b200_device_count() - opts->device));
+        // Partition: sample slices when every device still gets a GPU-filling number of rows -- each device
+        // then streams K/n rows per pass instead of all K -- else node shards with the histogram replicated.
+        // opts->reserved[2] = 2 forces node shards.
+        const bool tc = (opts->solver == GML_B200_SOLVER_AUTO && N + 1 > NEWTON_MAX_F) || opts->solver == GML_B200_SOLVER_FISTA_TC;
+        if (n_dev > 1 && tc && opts->reserved[2] != 2 && K / n_dev >= 65536 && opts->barrier_mu == 0.0) {
+            const int rc = learn_pairwise_multi_device_samples(counts, spins, K, N, ld, formulation, lambda, symmetrize, *opts,
+                                                               n_dev, out_theta, out_objective, stats);
+            if (rc >= 0) return rc;
+        }
         if (n_dev > 1 && N >= 2 * n_dev)
             return learn_pairwise_multi_device(counts, spins, K, N, ld, formulation, lambda, symmetrize, *opts, n_dev,
                                                out_theta, out_objective, stats);
@@ -813,6 +906,53 @@ int gml_b200_sample_gibbs_device(int32_t device, int32_t N, const int32_t* row_p
         GML_CUDA(cudaMemcpyAsync(jj.p, coupling, sizeof(float) * nnz, cudaMemcpyHostToDevice, st));
         GML_CUDA(cudaMemcpyAsync(hh.p, field ? field : hz.data(), sizeof(float) * N, cudaMemcpyHostToDevice, st));
         sample_gibbs(N, rp.p, ci.p, jj.p, hh.p, max_deg, n_samples, sweeps, seed, d_spins, ld, st);
+        GML_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int gml_b200_sample_gibbs_terms_device(int32_t device, int32_t N, int32_t order, int32_t n_terms, const int32_t* term_idx,
+                                       const float* term_weight, int64_t n_samples, int32_t sweeps, uint64_t seed,
+                                       int8_t* d_spins, int64_t ld, void* stream) {
+    return guarded([&] {
+        GML_REQUIRE(N >= 1 && N <= 4096 && order >= 1 && order <= 8 && n_terms >= 0 && term_idx && term_weight && d_spins,
+                    "bad sampler argument");
+        GML_REQUIRE(n_samples >= 1 && ld >= n_samples && sweeps >= 1, "bad sampler sizes");
+        GML_CUDA(cudaSetDevice(device));
+        cudaStream_t st = (cudaStream_t)stream;
+        // per-site incidence lists: (weight, the other members of the term)
+        const int width = std::max(1, order - 1);
+        std::vector<int32_t> row_ptr(N + 1, 0);
+        for (int t = 0; t < n_terms; ++t)
+            for (int m = 0; m < order; ++m) {
+                const int i = term_idx[(size_t)t * order + m];
+                if (i < 0) continue;
+                GML_REQUIRE(i < N, "sampler term refers to a spin >= N");
+                for (int m2 = 0; m2 < m; ++m2) GML_REQUIRE(term_idx[(size_t)t * order + m2] != i, "sampler term repeats a spin");
+                ++row_ptr[i + 1];
+            }
+        for (int i = 0; i < N; ++i) row_ptr[i + 1] += row_ptr[i];
+        const int nnz = row_ptr[N];
+        std::vector<int32_t> others((size_t)std::max(nnz, 1) * width, -1), fill(row_ptr.begin(), row_ptr.end() - 1);
+        std::vector<float> weight(std::max(nnz, 1), 0.f);
+        for (int t = 0; t < n_terms; ++t)
+            for (int m = 0; m < order; ++m) {
+                const int i = term_idx[(size_t)t * order + m];
+                if (i < 0) continue;
+                const int q = fill[i]++;
+                weight[q] = term_weight[t];
+                int w = 0;
+                for (int m2 = 0; m2 < order; ++m2) {
+                    const int j = term_idx[(size_t)t * order + m2];
+                    if (j >= 0 && m2 != m) others[(size_t)q * width + w++] = j;
+                }
+            }
+        DevBuf<int32_t> rp, ot;
+        DevBuf<float> ww;
+        rp.alloc(N + 1); ot.alloc(others.size()); ww.alloc(weight.size());
+        GML_CUDA(cudaMemcpyAsync(rp.p, row_ptr.data(), sizeof(int32_t) * (N + 1), cudaMemcpyHostToDevice, st));
+        GML_CUDA(cudaMemcpyAsync(ot.p, others.data(), sizeof(int32_t) * others.size(), cudaMemcpyHostToDevice, st));
+        GML_CUDA(cudaMemcpyAsync(ww.p, weight.data(), sizeof(float) * weight.size(), cudaMemcpyHostToDevice, st));
+        sample_gibbs_terms(N, width, rp.p, ot.p, ww.p, n_samples, sweeps, seed, d_spins, ld, st);
         GML_CUDA(cudaStreamSynchronize(st));
     });
 }

@@ -122,6 +122,8 @@ struct SolveResult {
     DevBuf<double> x;         // [Nn x Fp]
     DevBuf<double> objective; // [Nn]  f_u(x) + lambda*|x_pen|_1
     int iterations = 0, n_fg = 0, n_f = 0, n_unconverged = 0;
+    int n_stalled = 0;        // nodes accepted at the gradient noise floor with tol < residual <= 10 tol
+    int n_out_of_range = 0;   // nodes re-solved by the CUDA-core backend because they left the fixed-point range
     double max_residual = 0.0;
 };
 
@@ -157,6 +159,8 @@ struct EvalBackend {
     // [Nn x Fp] its gradient when want_grad.  lattice() > 0 means x must lie on that grid.
     virtual void eval(const double* x, bool want_grad, double* f_out, double* g_out, cudaStream_t st) = 0;
     virtual double lattice() const { return 0.0; }
+    // largest |x| the backend can represent at the current precision level (0 = unbounded)
+    virtual double x_range() const { return 0.0; }
     // precision level of the following passes: 0 = coarse (cheaper, coarser lattice), 1 = fine.  Returns
     // whether the requested level was taken (backends without levels always run fine).
     virtual bool set_level(int lv, cudaStream_t) { return lv == 1; }
@@ -194,14 +198,20 @@ void comm_unique_id(uint8_t* out128);
 Comm* comm_create(const uint8_t* id128, int rank, int world);
 void comm_destroy(Comm* c);
 int comm_world(const Comm* c);
+void comm_group_start(Comm* c);
+void comm_group_end(Comm* c);
 void comm_allreduce_sum_i64(Comm* c, long long* buf, size_t n, cudaStream_t st);
 void comm_allreduce_sum_f64(Comm* c, double* buf, size_t n, cudaStream_t st);
 void comm_allreduce_max_f64(Comm* c, double* buf, size_t n, cudaStream_t st);
 void comm_globalize_histogram(Comm* c, Histogram& h, cudaStream_t st);
+int comm_agree_max(Comm* c, int value, cudaStream_t st);
 
 // --- sampler.cu
 void sample_gibbs(int N, const int32_t* d_row_ptr, const int32_t* d_col, const float* d_J, const float* d_h,
                   int max_deg, int64_t n_samples, int sweeps, uint64_t seed, int8_t* d_spins, int64_t ld,
                   cudaStream_t st);
+
+void sample_gibbs_terms(int N, int width, const int32_t* d_row_ptr, const int32_t* d_others, const float* d_weight,
+                        int64_t n_samples, int sweeps, uint64_t seed, int8_t* d_spins, int64_t ld, cudaStream_t st);
 
 }  // namespace gml

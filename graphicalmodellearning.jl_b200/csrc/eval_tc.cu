@@ -209,6 +209,8 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_unsign
 //   coarse : lattice 2^-20, |x| < 1, 3 limbs (21 bits)      -- while the gradient mapping is >> the lattice
 constexpr double X_LATTICE_FINE = 1.0 / 16777216.0, X_LATTICE_COARSE = 1.0 / 1048576.0;
 constexpr int X_LIMBS_MAX = 4;
+// representable range of the balanced base-128 limbs: 3 limbs hold |q| <= 1040000 (x 2^-20), 4 limbs |q| <= 134000000 (x 2^-24)
+constexpr double X_RANGE_COARSE = 0.99, X_RANGE_FINE = 7.9;
 constexpr int NODE_TILE1 = 64;                   // nodes per energy tile (4 limbs -> N = 256)
 constexpr int NODE_TILE2 = 128;                  // nodes per gradient tile (M = 128)
 
@@ -914,6 +916,12 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
                     for (int w = 0; w < 4; ++w)
                         sw[w] = lds_u8(sa + 4 * w * 128) | (lds_u8(sa + (4 * w + 1) * 128) << 8) | (lds_u8(sa + (4 * w + 2) * 128) << 16) | (lds_u8(sa + (4 * w + 3) * 128) << 24);
                 }
+                // The 16 spin bytes of this thread are in registers: hand the slot back NOW.  Releasing it only after the
+                // block's math (as the first version did) chains the TMA producer -- which loads spin tile b+2 in order
+                // with the histogram tiles of block b+2 -- to the END of epilogue b, and the MMA warp then starts every
+                // block by waiting for histogram tiles (ncu: a third of its samples sat on full[stage] of k-block 0).
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sempty[slot]);
                 // ---- nodes 0..7 (in ra); nodes 8..15 start loading
                 epi_wait<XL>(ra);
                 epi_issue<XL>(tlane + as * 256 + 8, rb);
@@ -931,8 +939,6 @@ tc_energy_pair_kernel(const __grid_constant__ CUtensorMap tmA,    // P  [Kp x Fp
                     if (pre) { tc_fence_after(); epi_issue<XL>(tlane + as_n * 256, ra); }
                 }
                 energy_chunk_math<FORM, GRAD, XL, NR>(p, rb, sw[2], sw[3], scale_addr + 32, rgp, 8, wk, facc + 8);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sempty[slot]);
                 as = as_n; aphase = aphase_n; slot = slot_n; sphase = sphase_n;
                 if (pb + 1 < b1 && !pre) {
                     mbar_wait(&sfull[slot], sphase);
@@ -1325,6 +1331,7 @@ struct BackendTC : EvalBackend {
     }
 
     double lattice() const override { return level == 0 ? X_LATTICE_COARSE : X_LATTICE_FINE; }
+    double x_range() const override { return level == 0 ? X_RANGE_COARSE : X_RANGE_FINE; }
     // rounding noise of a gradient component: ~0.29 sqrt(K) wmax e^B / qmax(nr); e^B ~ 20 as a typical upper value
     double grad_noise() const override {
         const Histogram& h = *p.hist;
@@ -1460,8 +1467,10 @@ struct BackendTC : EvalBackend {
             span_end(st);
         }
         if (p.comm) {   // sample-sharded: exact int64 gradient sums and fp64 objective sums across the ranks
+            comm_group_start(p.comm);
             comm_allreduce_sum_f64(p.comm, fsum.p, pad1, st);
             if (want_grad) comm_allreduce_sum_i64(p.comm, G64.p, (size_t)pad2 * p.Fp, st);
+            comm_group_end(p.comm);
         }
         tc_finalize_kernel<<<n_nodes, 128, 0, st>>>(p.form, p.Fp, fsum.p, G64.p, delta.p, f_out, g_out, want_grad ? 1 : 0, act_idx);
         GML_LAUNCHED();

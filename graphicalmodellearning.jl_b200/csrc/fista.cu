@@ -30,12 +30,15 @@ namespace {
 struct FistaState {
     int Nn, Fp, form;
     double lambda, tol, lattice_inv, lattice, eps_f, eps_g;
+    double x_range;   // lattice backends: largest representable |x| at the current precision level (0 = unbounded)
     const uint8_t* pen;
     double *X, *Z, *Y, *Yn, *G, *Gn;
     double *fY, *fYn, *L, *t, *tn, *q, *c, *gmap, *obj;
     double* best;     // smallest gradient-mapping norm seen
     int *stall, *streak;
-    int* status;      // 0 active, 1 converged, 2 stalled at the gradient noise floor, 3 parked (done with the coarse level)
+    int* status;      // 0 active, 1 converged, 2 stalled at the gradient noise floor, 3 parked (done with the coarse level),
+                      // 4 left the fixed-point range of the backend on the fine level (re-solved by the unbounded backend)
+    int* clamped;     // [Nn] raised by the trial kernel when a prox point had to be clamped to the backend's range
     double park_tol;  // coarse level: a node whose gradient-mapping norm is below this waits for the fine level
     int* n_active;
     unsigned long long* gmax;   // bits of the largest gradient-mapping norm over the active nodes of this round
@@ -62,8 +65,14 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 }
 
 __device__ __forceinline__ double snap(double v, const FistaState& s) {
-    // lattice backends hold x as a 28-bit fixed-point number: |x| < 8
-    return s.lattice_inv > 0.0 ? rint(fmin(fmax(v, -7.9), 7.9) * s.lattice_inv) * s.lattice : v;
+    // lattice backends hold x as a fixed-point number with a bounded range (|x| < 7.9 on the fine level of the
+    // tensor-core backend).  A point that had to be clamped is NOT the prox point: callers record it (snap_flag) and the
+    // node is never retired with it.
+    return s.lattice_inv > 0.0 ? rint(fmin(fmax(v, -s.x_range), s.x_range) * s.lattice_inv) * s.lattice : v;
+}
+__device__ __forceinline__ double snap_flag(double v, const FistaState& s, bool& clamped) {
+    if (s.lattice_inv > 0.0 && fabs(v) > s.x_range) clamped = true;
+    return snap(v, s);
 }
 
 // Z = prox step from (Y, G);  Y' = Z + beta (Z - X);  model terms of the descent test at Y'
@@ -74,6 +83,7 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
     const double L = s.L[u], thr = s.lambda / L;
     const int64_t o = (int64_t)u * s.Fp;
     double dm = 0.0, r = 0.0;
+    bool clamped = false;
     for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
         const uint8_t pc = s.pen[o + f];
         const double y = s.Y[o + f], g = s.G[o + f];
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
         if (pc != PEN_ZERO) {
             z = y - g / L;
             if (pc == PEN_L1) { const double a = fabs(z) - thr; z = a > 0.0 ? copysign(a, z) : 0.0; }
-            z = snap(z, s);
+            z = snap_flag(z, s, clamped);
         }
         s.Z[o + f] = z;
         dm = fmax(dm, fabs(z - y));
@@ -96,12 +106,13 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
     double q1 = 0.0, q2 = 0.0;
     for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
         const double z = s.Z[o + f], y = s.Y[o + f];
-        const double yn = snap(z + beta * (z - s.X[o + f]), s);
+        const double yn = snap_flag(z + beta * (z - s.X[o + f]), s, clamped);
         s.Yn[o + f] = yn;
         const double d = yn - y;
         q1 += s.G[o + f] * d; q2 += d * d;
     }
     q1 = block_sum(q1, red); q2 = block_sum(q2, red);
+    if (__syncthreads_or(clamped ? 1 : 0) && threadIdx.x == 0) s.clamped[u] = 1;
     if (threadIdx.x == 0) {
         s.q[u] = q1 + 0.5 * L * q2;
         s.c[u] = 0.5 * L * q2;
@@ -113,9 +124,20 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
 
 __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
     const int u = blockIdx.x;
-    if (s.status[u]) return;
+    // every thread reads the status before any thread of the block may change it
+    const int status0 = s.status[u];
+    const int was_clamped = s.clamped[u];
+    __syncthreads();
+    if (status0) return;
     const int64_t o = (int64_t)u * s.Fp;
     const double gm = s.gmap[u];
+    // The iterate left the representable range of the lattice backend: its trial points are clamped, not prox points.
+    // Coarse level: handled by the driver (range overflow -> fine level).  Fine level: the node leaves the passes with
+    // status 4 at its last accepted point and is re-solved by the unbounded CUDA-core backend (solve_fista).
+    if (was_clamped && s.fine) {
+        if (threadIdx.x == 0) s.status[u] = 4;
+        return;
+    }
     // ---- convergence is decided at Y (whose gradient is known): the prox point Z is the answer
     // (on a lattice backend a prox step of at most one lattice unit is the finest resolvable fixed point; nodes never
     // retire on the coarse precision level, whose lattice and gradient noise are above the tolerance)
@@ -151,7 +173,14 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
     // curvature) and, for the function-value form, against the noise.
     const bool reject = !isfinite(fN) || !isfinite(dot) || (c > 0.0 && D < -(0.1 * c + (measurable ? noise : 0.0)));
     if (reject) {
-        if (threadIdx.x == 0) { s.L[u] *= 2.0; s.streak[u] = 0; atomicAdd(s.n_active, 1); }
+        // D/c = 1 - L_dir/L: when the violation was measured, jump to just above the directional curvature instead of
+        // doubling blindly (the first rounds of a cold start, where L0 underestimates the curvature by 3-4x, cost one
+        // rejected pass instead of two); bounded to [2, 8] L
+        if (threadIdx.x == 0) {
+            double grow = 2.0;
+            if (isfinite(D) && c > 0.0 && (measurable || secant_ok)) grow = fmin(fmax(1.1 * (1.0 - D / c), 2.0), 8.0);
+            s.L[u] *= grow; s.streak[u] = 0; atomicAdd(s.n_active, 1);
+        }
         return;
     }
     int stall = s.stall[u];
@@ -183,7 +212,13 @@ __global__ void fista_init_kernel(FistaState s, double L0) {
     if (u >= s.Nn) return;
     s.L[u] = L0 > 0.0 ? L0 : s.L[u] * -L0;      // first level: initial estimate; later levels: rescale by rho ratio
     s.t[u] = 1.0; s.status[u] = 0; s.gmap[u] = 1e300; s.obj[u] = 0.0;
-    s.best[u] = 1e300; s.stall[u] = 0; s.streak[u] = 0;
+    s.best[u] = 1e300; s.stall[u] = 0; s.streak[u] = 0; s.clamped[u] = 0;
+}
+
+// start point of a warm-started solve -> the lattice / range of the precision level it is first evaluated on
+__global__ void fista_snap_kernel(FistaState s, double* __restrict__ x, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = snap(x[i], s);
 }
 
 // parked nodes rejoin (fine level): state kept, stall counters reset
@@ -229,7 +264,9 @@ __global__ void __launch_bounds__(128) fista_objective_kernel(FistaState s, cons
 
 }  // namespace
 
-void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, SolveResult& r, cudaStream_t st) {
+namespace {
+void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backend, SolveResult& r, std::vector<int>& out_of_range,
+                      cudaStream_t st) {
     const int Nn = prob.Nn, Fp = prob.Fp;
     auto tick = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = tick();
@@ -238,14 +275,14 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     be->set_profiling(o.reserved[0] != 0);
     const size_t nx = (size_t)Nn * Fp;
     DevBuf<double> Z, Y, Yn, G, Gn, fY, fYn, L, t, tn, q, c, gmap, best;
-    DevBuf<int> status, n_active, stall, streak;
+    DevBuf<int> status, n_active, stall, streak, clamped;
     DevBuf<unsigned long long> gmax;
     DevBuf<int> act_idx;     // compacted list of the active nodes
     act_idx.alloc(Nn);
     r.x.alloc(nx); r.objective.alloc(Nn);
     Z.alloc(nx); Y.alloc(nx); Yn.alloc(nx); G.alloc(nx); Gn.alloc(nx);
     fY.alloc(Nn); fYn.alloc(Nn); L.alloc(Nn); t.alloc(Nn); tn.alloc(Nn); q.alloc(Nn); c.alloc(Nn); gmap.alloc(Nn);
-    status.alloc(Nn); n_active.alloc(1); best.alloc(Nn); stall.alloc(Nn); streak.alloc(Nn); gmax.alloc(1);
+    status.alloc(Nn); n_active.alloc(1); best.alloc(Nn); stall.alloc(Nn); streak.alloc(Nn); gmax.alloc(1); clamped.alloc(Nn);
     if (prob.x0) GML_CUDA(cudaMemcpyAsync(r.x.p, prob.x0, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
     else GML_CUDA(cudaMemsetAsync(r.x.p, 0, nx * sizeof(double), st));
     GML_CUDA(cudaMemsetAsync(Y.p, 0, nx * sizeof(double), st));
@@ -257,7 +294,7 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
     s.lattice = be->lattice();
     s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
     s.eps_f = 1e-6;   // generous upper bound of the evaluation noise of f
-    s.best = best.p; s.stall = stall.p; s.streak = streak.p;
+    s.best = best.p; s.stall = stall.p; s.streak = streak.p; s.clamped = clamped.p;
     s.pen = prob.pen.p;
     s.X = r.x.p; s.Z = Z.p; s.Y = Y.p; s.Yn = Yn.p; s.G = G.p; s.Gn = Gn.p;
     s.fY = fY.p; s.fYn = fYn.p; s.L = L.p; s.t = t.p; s.tn = tn.p; s.q = q.p; s.c = c.p; s.gmap = gmap.p;
@@ -300,12 +337,21 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
         // it reaches the tolerance or the resolution of that lattice, where it parks; when all have parked, the last
         // rounds run at full precision.  Coarse-lattice points are fine-lattice points: the switch only refreshes (f, G).
         int level = (o.reserved[3] == 0 && user_tol <= 1e-4 && be->set_level(0, st)) ? 0 : 1;
-        if (level == 1) be->set_level(1, st);
+        be->set_level(1, st);
+        s.x_range = be->x_range();          // the clamp is the FINE level's range on both levels: the coarse level's own
+        if (level == 0) be->set_level(0, st);   // (smaller) range is watched by its quantiser, which raises device_flags()
         auto sync_level = [&] {
             s.fine = level; s.lattice = be->lattice(); s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
             s.eps_g = be->grad_noise() * scale;
         };
         sync_level();
+        if (prob.x0 && li == 0 && s.lattice > 0.0) {
+            // a warm start (e.g. the previous point of a lambda path, on the fine lattice) is first evaluated on this
+            // level's lattice: move X and Y there, so that the stored (f, G) belong to the point the driver holds
+            fista_snap_kernel<<<(unsigned)ceil_div((int64_t)nx, 256), 256, 0, st>>>(s, r.x.p, (int64_t)nx);
+            GML_LAUNCHED();
+            GML_CUDA(cudaMemcpyAsync(Y.p, r.x.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
         // Active-set compaction: once the active nodes fill at most 7/8 of the slots of the current pass, the passes are
         // restricted to the active nodes (ordered list built on the device; the host knows the count from its per-round
         // read).  Parked / converged nodes in the list stay as dead slots until the next compaction.
@@ -438,11 +484,72 @@ void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, S
                 fprintf(stderr, "[gml_b200] node %d status %d L %.6g t %.4g gmap %.3e q %.3e c %.3e fY %.17g fX %.17g\n",
                         u, hs[u], hL[u], ht[u], hg[u], hq[u], hc[u], hfY[u], hfN[u]);
     }
-    double mr = 0.0; int unconv = 0;
-    // a node stalled at the gradient noise floor counts as converged when it is within 10x tol
-    for (int u = 0; u < Nn; ++u) { mr = std::max(mr, hg[u]); unconv += (hs[u] == 1 || (hs[u] == 2 && hg[u] <= 10.0 * s.tol)) ? 0 : 1; }
+    double mr = 0.0; int unconv = 0, stalled = 0;
+    // A node whose gradient mapping stopped improving above tol (status 2: the noise floor of the backend's gradient)
+    // is accepted when it is within 10x tol and REPORTED in n_stalled / max_residual (gml_b200_stats); beyond that, or
+    // when max_iter ran out, it is unconverged (GML_B200_ENOTCONV).  Status 4 nodes are handed to the caller.
+    for (int u = 0; u < Nn; ++u) {
+        if (hs[u] == 4) { out_of_range.push_back(u); continue; }
+        mr = std::max(mr, hg[u]);
+        if (hs[u] == 2 && hg[u] <= 10.0 * s.tol) ++stalled;
+        else if (hs[u] != 1) ++unconv;
+    }
     be->collect_profile(r.profile);
-    r.iterations = it; r.n_fg = n_fg; r.n_f = n_f; r.n_unconverged = unconv; r.max_residual = mr;
+    r.iterations = it; r.n_fg = n_fg; r.n_f = n_f; r.n_unconverged = unconv; r.n_stalled = stalled; r.max_residual = mr;
+}
+
+__global__ void gather_subproblem_kernel(const int* __restrict__ idx, int Fp, const int32_t* __restrict__ spin_row, const uint8_t* __restrict__ pen,
+                                         const double* __restrict__ x, int32_t* __restrict__ spin_row_s, uint8_t* __restrict__ pen_s,
+                                         double* __restrict__ x_s) {
+    const int j = blockIdx.x, u = idx[j];
+    if (threadIdx.x == 0) spin_row_s[j] = spin_row[u];
+    for (int f = threadIdx.x; f < Fp; f += blockDim.x) {
+        pen_s[(int64_t)j * Fp + f] = pen[(int64_t)u * Fp + f];
+        x_s[(int64_t)j * Fp + f] = x[(int64_t)u * Fp + f];
+    }
+}
+__global__ void scatter_subsolution_kernel(const int* __restrict__ idx, int Fp, const double* __restrict__ x_s, const double* __restrict__ obj_s,
+                                           double* __restrict__ x, double* __restrict__ obj) {
+    const int j = blockIdx.x, u = idx[j];
+    if (threadIdx.x == 0) obj[u] = obj_s[j];
+    for (int f = threadIdx.x; f < Fp; f += blockDim.x) x[(int64_t)u * Fp + f] = x_s[(int64_t)j * Fp + f];
+}
+}  // namespace
+
+// Front end: the tensor-core backend holds the iterate as a fixed-point number (|x| < 7.9).  Nodes whose optimum lies
+// beyond that (near-deterministic couplings: the L1 optimum grows like -log lambda) leave its passes with status 4 and
+// are re-solved here, warm-started from their last accepted point, by the CUDA-core backend, which has no such bound --
+// the reference's Ipopt has none either (src/GraphicalModelLearning.jl:169-177).
+void solve_fista(const NodeProblem& prob, const gml_b200_opts& o, int backend, SolveResult& r, cudaStream_t st) {
+    std::vector<int> oor;
+    solve_fista_impl(prob, o, backend, r, oor, st);
+    if (oor.empty()) return;
+    GML_REQUIRE(backend == GML_B200_SOLVER_FISTA_TC && prob.comm == nullptr,
+                "an iterate left the representable range of the solver backend");
+    if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista: %zu node(s) left the fixed-point range |x| < 7.9: re-solving them with the CUDA-core backend\n", oor.size());
+    const int n = (int)oor.size(), Fp = prob.Fp;
+    DevBuf<int> idx;
+    DevBuf<double> x0;
+    idx.alloc(n); x0.alloc((size_t)n * Fp);
+    GML_CUDA(cudaMemcpyAsync(idx.p, oor.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    NodeProblem sub;
+    sub.hist = prob.hist; sub.Q = prob.Q; sub.F = prob.F; sub.Fp = Fp; sub.form = prob.form; sub.lambda = prob.lambda; sub.Nn = n;
+    sub.spin_row.alloc(n); sub.pen.alloc((size_t)n * Fp);
+    gather_subproblem_kernel<<<n, 128, 0, st>>>(idx.p, Fp, prob.spin_row.p, prob.pen.p, r.x.p, sub.spin_row.p, sub.pen.p, x0.p);
+    GML_LAUNCHED();
+    sub.x0 = x0.p;
+    SolveResult rs;
+    std::vector<int> none;
+    solve_fista_impl(sub, o, GML_B200_SOLVER_FISTA_CC, rs, none, st);
+    scatter_subsolution_kernel<<<n, 128, 0, st>>>(idx.p, Fp, rs.x.p, rs.objective.p, r.x.p, r.objective.p);
+    GML_LAUNCHED();
+    GML_CUDA(cudaStreamSynchronize(st));
+    r.n_fg += rs.n_fg; r.n_f += rs.n_f;
+    if (r.fg_units >= 0.0) r.fg_units += (rs.fg_units >= 0.0 ? rs.fg_units : rs.n_fg) * (double)n / prob.Nn;
+    r.iterations += rs.iterations;
+    r.n_unconverged += rs.n_unconverged; r.n_stalled += rs.n_stalled;
+    r.n_out_of_range = n;
+    r.max_residual = std::max(r.max_residual, rs.max_residual);
 }
 
 }  // namespace gml

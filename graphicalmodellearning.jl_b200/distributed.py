@@ -87,3 +87,58 @@ def upload_replicated(session, counts, spins, group=None):
     torch.cuda.current_stream().synchronize()
     session.attach_device(d_counts.data_ptr(), full.data_ptr(), k, n, k)
     return session
+
+
+# ---- sample-sharded partition (secondary): histogram ROWS split over the ranks, every rank advances all
+# node problems in lockstep; per pass the int64 gradient sums and the fp64 objective sums are all-reduced by the
+# library's own NCCL communicator (csrc/comm.cu).  Each rank streams only K/world samples per pass (node shards stream
+# the whole replicated histogram on every rank), so it is also the cheaper partition whenever K/world still fills the
+# GPU -- measured at C3: profiles/r2_*.
+def sample_slice(n_rows: int, world: int, rank: int, align: int = 256) -> Tuple[int, int]:
+    """Histogram rows [begin, end) of rank: equal parts, cuts on multiples of `align` (CTA pairs sweep 2 x 128 rows)."""
+    per = -(-n_rows // world)
+    per = -(-per // align) * align
+    return min(n_rows, rank * per), min(n_rows, (rank + 1) * per)
+
+
+def upload_sample_sharded(session, counts, spins, group=None):
+    """Make this rank's slice of the histogram resident (ONE H2D of K/world rows per rank, no collective), create the
+    library communicator over `group` and make the weights global.  counts f64 [K], spins int8 [N x K] spin-major
+    host arrays (pinned for full H2D speed) holding the same data on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    t_spins = spins if isinstance(spins, torch.Tensor) else torch.from_numpy(spins)
+    t_counts = counts if isinstance(counts, torch.Tensor) else torch.from_numpy(counts)
+    n, k = t_spins.shape
+    b, e = sample_slice(k, world, rank)
+    if e <= b:
+        raise ValueError("sample-sharded upload: fewer histogram rows than ranks")
+    dev = torch.device(f"cuda:{session.device}")
+    part = torch.empty((n, e - b), dtype=torch.int8, device=dev)
+    part.copy_(t_spins[:, b:e], non_blocking=True)               # strided 2-D copy: N rows of (e-b) contiguous bytes
+    d_counts = t_counts[b:e].to(dev, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    session.attach_device(d_counts.data_ptr(), part.data_ptr(), e - b, n, e - b)
+    if world > 1:
+        session.comm_init(group)
+    return session
+
+
+def learn_sample_sharded(session, formulation, method, symmetrize: bool = True) -> torch.Tensor:
+    """learn() for a pairwise formulation on a sample-sharded session (upload_sample_sharded): every rank solves all
+    nodes and ends with the same N x N device matrix (row-major); no gather."""
+    import ctypes
+    import dataclasses
+    from . import _lib
+    n = session.N
+    sharded = dist.is_initialized() and dist.get_world_size() > 1
+    m = dataclasses.replace(method, sample_sharded=sharded)
+    rows = torch.empty((n, n), dtype=torch.float64, device=f"cuda:{session.device}")
+    stream = torch.cuda.current_stream().cuda_stream
+    try:
+        session.solve_pairwise_device(formulation, m, rows.data_ptr(), 0, n, stream=stream)
+    finally:
+        method.last_stats = m.last_stats
+    if symmetrize:
+        _lib.check(_lib.load().gml_b200_symmetrize_device(ctypes.c_void_p(rows.data_ptr()), n, ctypes.c_void_p(stream)))
+    return rows

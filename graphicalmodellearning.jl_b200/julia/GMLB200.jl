@@ -34,7 +34,7 @@ mutable struct GMLB200Stats
     n_fg_passes::Int32
     n_f_passes::Int32
     n_unconverged::Int32
-    reserved_i::Int32
+    n_stalled::Int32
     kernel_launches::Int64
     evals::Cdouble
     pack_ms::Cdouble

@@ -43,10 +43,13 @@ extern "C" {
 #define GML_B200_SOLVER_AUTO 0
 #define GML_B200_SOLVER_NEWTON 1   /* fp64 proximal-Newton, features <= 64 (small problems)        */
 #define GML_B200_SOLVER_FISTA_CC 2 /* batched FISTA, CUDA-core fp32 contractions                   */
-#define GML_B200_SOLVER_FISTA_TC 3 /* batched FISTA, tcgen05 (int8 limb) tensor-core contractions  */
+#define GML_B200_SOLVER_FISTA_TC 3 /* batched FISTA, tcgen05 (int8 limb) tensor-core contractions.  The iterate is a
+                                      fixed-point number with |x| < 7.9; a node whose optimum lies beyond that range is
+                                      detected and re-solved by the FISTA_CC backend inside the same call            */
 
 typedef struct gml_b200_opts {
-    double tol;         /* stopping tolerance (max-norm of prox-gradient mapping / Newton step); default 1e-6 FISTA, 1e-12 Newton */
+    double tol;         /* stopping tolerance (max-norm of prox-gradient mapping / Newton step); default 1e-6 FISTA, 1e-12 Newton.
+                           FISTA accepts a node that stalls at the gradient noise floor within 10*tol: see gml_b200_stats.n_stalled */
     double barrier_mu;  /* 0 = exact L1 minimiser; > 0 = Ipopt-compatible log-barrier point at this mu (Newton solver only) */
     int32_t max_iter;   /* default 5000 */
     int32_t solver;     /* GML_B200_SOLVER_* */
@@ -71,8 +74,10 @@ typedef struct gml_b200_stats {
     int32_t iterations;       /* outer iterations (max over nodes) */
     int32_t n_fg_passes;      /* full objective+gradient passes over the histogram */
     int32_t n_f_passes;       /* objective-only passes */
-    int32_t n_unconverged;    /* nodes that missed tol */
-    int32_t reserved_i;
+    int32_t n_unconverged;    /* nodes that missed tol (the call then returns GML_B200_ENOTCONV) */
+    int32_t n_stalled;        /* FISTA: nodes whose gradient mapping stopped improving at the backend's gradient noise floor
+                                 with tol < residual <= 10*tol; they are ACCEPTED (not counted in n_unconverged) and their
+                                 residual is part of max_residual -- callers that need tol strictly check n_stalled == 0 */
     int64_t kernel_launches;  /* kernels of this library launched by the call */
     double evals;             /* node*sample evals = nodes*K*(fg + 0.5*f), passes weighted by the fraction of
                                  the histogram they swept (coarse continuation levels count 1/stride)   */
@@ -173,6 +178,13 @@ int gml_b200_symmetrize_device(double* d_theta, int32_t N, void* stream);
 int gml_b200_sample_gibbs_device(int32_t device, int32_t N, const int32_t* row_ptr, const int32_t* col_idx,
                                  const float* coupling, const float* field, int64_t n_samples,
                                  int32_t sweeps, uint64_t seed, int8_t* d_spins, int64_t ld, void* stream);
+
+/* Same for general +-1 models p(s) ~ exp(sum_t w_t prod_{i in t} s_i) -- the distribution the reference's `sample`
+ * enumerates for order > 2 (src/sampling.jl:58-88); generates the 3-body inputs of the multiRISE benchmark config.
+ * term_idx: n_terms x order 0-based spin ids, -1 padded (a term of length 1 is a field); term_weight[n_terms]. */
+int gml_b200_sample_gibbs_terms_device(int32_t device, int32_t N, int32_t order, int32_t n_terms, const int32_t* term_idx,
+                                       const float* term_weight, int64_t n_samples, int32_t sweeps, uint64_t seed,
+                                       int8_t* d_spins, int64_t ld, void* stream);
 
 /* ---- sample-sharded mode: histogram rows split over ranks, every rank solves all nodes; per pass
  * the int64 gradient sums and fp64 objective sums are combined with NCCL all-reduces on the solve stream.

@@ -74,9 +74,68 @@ static double eval_f(const node_problem* p, const double* x) {
     return acc;
 }
 
+/* Threads used INSIDE one node's f/g/H accumulation (split over histogram rows).  The node loops of the
+ * learn_* entry points set it to (host threads) / (nodes solved concurrently), so that a test which asks for a
+ * few nodes of a large problem still uses the whole box.  Partial sums are combined in thread order. */
+static int g_inner_threads = 1;
+
+static double eval_fgh_rows(const node_problem* p, const double* x, double* g, double* H, double* row,
+                            int64_t k0, int64_t k1, double tmax);
+
 /* f, g (F), H (F x F, full symmetric).  `row` is scratch of F doubles. */
 static double eval_fgh(const node_problem* p, const double* x, double* g, double* H, double* row) {
     const int F = p->F;
+#ifdef _OPENMP
+    if (g_inner_threads > 1 && p->K >= 8192) {
+        const int T = g_inner_threads;
+        double tmax = 0.0;
+        if (p->form == FORM_LOGRISE) {
+            tmax = -INFINITY;
+#pragma omp parallel for num_threads(T) reduction(max : tmax)
+            for (int64_t k = 0; k < p->K; ++k) {
+                const int8_t* s = p->stat + k * F;
+                double t = 0.0;
+                for (int f = 0; f < F; ++f) t += x[f] * s[f];
+                if (-t > tmax) tmax = -t;
+            }
+        }
+        double* gs = malloc(sizeof(double) * (size_t)T * F);
+        double* Hs = malloc(sizeof(double) * (size_t)T * F * F);
+        double* accs = malloc(sizeof(double) * T);
+        int granted = 1;                      /* the runtime may grant fewer threads than asked for (nested regions) */
+#pragma omp parallel num_threads(T)
+        {
+            const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#pragma omp single
+            granted = nt;
+            double* rw = malloc(sizeof(double) * F);
+            const int64_t k0 = p->K * t / nt, k1 = p->K * (t + 1) / nt;
+            accs[t] = eval_fgh_rows(p, x, gs + (size_t)t * F, Hs + (size_t)t * F * F, rw, k0, k1, tmax);
+            free(rw);
+        }
+        double acc = 0.0;
+        memset(g, 0, sizeof(double) * F);
+        memset(H, 0, sizeof(double) * (size_t)F * F);
+        for (int t = 0; t < granted; ++t) {
+            acc += accs[t];
+            for (int f = 0; f < F; ++f) g[f] += gs[(size_t)t * F + f];
+            for (size_t i = 0; i < (size_t)F * F; ++i) H[i] += Hs[(size_t)t * F * F + i];
+        }
+        free(gs); free(Hs); free(accs);
+        double fval = acc;
+        if (p->form == FORM_LOGRISE) {
+            const double Z = acc;
+            for (int f = 0; f < F; ++f) g[f] /= Z;
+            for (int a = 0; a < F; ++a)
+                for (int b = 0; b <= a; ++b) H[(size_t)a * F + b] = H[(size_t)a * F + b] / Z - g[a] * g[b];
+            fval = log(Z) + tmax;
+        }
+        for (int a = 0; a < F; ++a)
+            for (int b = 0; b < a; ++b) H[(size_t)b * F + a] = H[(size_t)a * F + b];
+        (void)row;
+        return fval;
+    }
+#endif
     memset(g, 0, sizeof(double) * F);
     memset(H, 0, sizeof(double) * (size_t)F * F);
     double acc = 0.0, tmax = 0.0;
@@ -125,6 +184,41 @@ static double eval_fgh(const node_problem* p, const double* x, double* g, double
     for (int a = 0; a < F; ++a)
         for (int b = 0; b < a; ++b) H[(size_t)b * F + a] = H[(size_t)a * F + b];
     return fval;
+}
+
+/* un-normalised sums of eval_fgh over the histogram rows [k0, k1) (lower triangle of H only) */
+static double eval_fgh_rows(const node_problem* p, const double* x, double* g, double* H, double* row,
+                            int64_t k0, int64_t k1, double tmax) {
+    const int F = p->F;
+    memset(g, 0, sizeof(double) * F);
+    memset(H, 0, sizeof(double) * (size_t)F * F);
+    double acc = 0.0;
+    for (int64_t k = k0; k < k1; ++k) {
+        const int8_t* s = p->stat + k * F;
+        double t = 0.0;
+        for (int f = 0; f < F; ++f) t += x[f] * s[f];
+        double gw, hw;
+        if (p->form == FORM_RISE) {
+            double e = p->w[k] * exp(-t);
+            acc += e; gw = e; hw = e;
+        } else if (p->form == FORM_LOGRISE) {
+            double e = p->w[k] * exp(-t - tmax);
+            acc += e; gw = e; hw = e;
+        } else {
+            double a = -2.0 * t;
+            acc += p->w[k] * ((a > 0 ? a : 0.0) + log1p(exp(-fabs(a))));
+            double sig = 0.5 * (1.0 - tanh(t));
+            gw = 2.0 * p->w[k] * sig;
+            hw = 4.0 * p->w[k] * sig * (1.0 - sig);
+        }
+        for (int f = 0; f < F; ++f) { g[f] -= gw * s[f]; row[f] = hw * s[f]; }
+        for (int a = 0; a < F; ++a) {
+            double* Ha = H + (size_t)a * F;
+            const double sa = (double)s[a];
+            for (int b = 0; b <= a; ++b) Ha[b] += sa * row[b];
+        }
+    }
+    return acc;
 }
 
 static double l1_pen(const double* x, const uint8_t* pen, int F) {
@@ -299,6 +393,20 @@ int gml_oracle_solve_node(int form, const int8_t* stat, const double* w, int64_t
  * When the node range is the full range and symmetrize != 0, out is symmetrised (:184-186).
  * stats[0] = sum of f/g/H evaluations, stats[1] = sum of f-only evaluations (over nodes).
  */
+/* host threads = (nodes solved concurrently) x (threads inside a node's accumulation) */
+static int split_threads(int n_nodes) {
+#ifdef _OPENMP
+    const int T = omp_get_max_threads();
+    int outer = n_nodes < T ? (n_nodes > 0 ? n_nodes : 1) : T;
+    g_inner_threads = T / outer > 1 ? T / outer : 1;
+    omp_set_max_active_levels(2);
+    return outer;
+#else
+    (void)n_nodes;
+    return 1;
+#endif
+}
+
 int gml_oracle_learn_pairwise(const double* counts, const int8_t* spins, int64_t K, int N, int64_t ld,
                               int form, double lam, int symmetrize, int mode, double mu,
                               int node_begin, int node_end, double* out, double* obj, int64_t* stats) {
@@ -307,7 +415,9 @@ int gml_oracle_learn_pairwise(const double* counts, const int8_t* spins, int64_t
     double* w = malloc(sizeof(double) * K);
     for (int64_t k = 0; k < K; ++k) w[k] = counts[k] / M;
     int64_t tot_fgh = 0, tot_f = 0;
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : tot_fgh, tot_f)
+    const int outer = split_threads(node_end - node_begin);
+    (void)outer;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : tot_fgh, tot_f) num_threads(outer)
     for (int u = node_begin; u < node_end; ++u) {
         int8_t* stat = malloc((size_t)K * N);
         uint8_t* pen = malloc(N);
@@ -333,6 +443,7 @@ int gml_oracle_learn_pairwise(const double* counts, const int8_t* spins, int64_t
             }
     }
     if (stats) { stats[0] = tot_fgh; stats[1] = tot_f; }
+    g_inner_threads = 1;
     free(w);
     return 0;
 }
@@ -343,15 +454,19 @@ int gml_oracle_learn_pairwise(const double* counts, const int8_t* spins, int64_t
  * (0-based spin ids, -1 padded), key_len[n_keys], listed in the reference's own order
  * ((u,), (u,j)..., (u,j<k)...).  out_vals[u * n_keys + f].  L1 on keys of length > 1 (:118).
  */
-int gml_oracle_learn_multibody(const double* counts, const int8_t* spins, int64_t K, int N, int64_t ld,
-                               int order, int n_keys, const int32_t* key_idx, const int32_t* key_len,
-                               double lam, int mode, double mu, double* out_vals, double* obj) {
+int gml_oracle_learn_multibody_nodes(const double* counts, const int8_t* spins, int64_t K, int N, int64_t ld,
+                                     int order, int n_keys, const int32_t* key_idx, const int32_t* key_len,
+                                     double lam, int mode, double mu, int node_begin, int node_end,
+                                     double* out_vals, double* obj) {
     double M = 0.0;
     for (int64_t k = 0; k < K; ++k) M += counts[k];
     double* w = malloc(sizeof(double) * K);
     for (int64_t k = 0; k < K; ++k) w[k] = counts[k] / M;
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int u = 0; u < N; ++u) {
+    (void)N;
+    const int outer = split_threads(node_end - node_begin);
+    (void)outer;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(outer)
+    for (int u = node_begin; u < node_end; ++u) {
         int8_t* stat = malloc((size_t)K * n_keys);
         uint8_t* pen = malloc(n_keys);
         double* x = malloc(sizeof(double) * n_keys);
@@ -371,7 +486,148 @@ int gml_oracle_learn_multibody(const double* counts, const int8_t* spins, int64_
         if (obj) obj[u] = o;
         free(stat); free(pen); free(x);
     }
+    g_inner_threads = 1;
     free(w);
+    return 0;
+}
+
+int gml_oracle_learn_multibody(const double* counts, const int8_t* spins, int64_t K, int N, int64_t ld,
+                               int order, int n_keys, const int32_t* key_idx, const int32_t* key_len,
+                               double lam, int mode, double mu, double* out_vals, double* obj) {
+    return gml_oracle_learn_multibody_nodes(counts, spins, K, N, ld, order, n_keys, key_idx, key_len, lam, mode, mu,
+                                            0, N, out_vals, obj);
+}
+
+/*
+ * Objective and gradient of the smooth part f_u at caller-supplied points, WITHOUT solving: the float64 statement of
+ *   RISE    f_u = sum_k w_k exp(-t_k)            src/GraphicalModelLearning.jl:170   (gradient: :199-208)
+ *   logRISE f_u = log sum_k w_k exp(-t_k)        src/GraphicalModelLearning.jl:279
+ *   RPLE    f_u = sum_k w_k log(1+exp(-2 t_k))   src/GraphicalModelLearning.jl:317
+ * with t_k = s_u^k (sum_{i != u} x_i s_i^k + x_field)  (nodal_stat of :162 folded in), w_k = c_k / M (:79).
+ * nodes[n_nodes]: 0-based node ids; x, g_out: n_nodes x (N+1) row-major in the order of the C ABI's
+ * gml_b200_eval_pairwise (couplings to spins 0..N-1, the self entry ignored / returned as 0, then the field).
+ * Used by the parity tests at sizes where a per-node K x N float64 nodal_stat matrix is too slow, and by bench.py's
+ * KKT check of the solution it times.  The histogram is swept once per node in cache-sized row chunks, threads
+ * split the rows, partial sums are combined in thread order (deterministic for a fixed thread count).
+ */
+int gml_oracle_eval_pairwise(const double* counts, const int8_t* spins, int64_t K, int N, int64_t ld, int form,
+                             const int32_t* nodes, int n_nodes, const double* x, double* f_out, double* g_out) {
+    double M = 0.0;
+    for (int64_t k = 0; k < K; ++k) M += counts[k];
+    int T = 1;
+#ifdef _OPENMP
+    T = omp_get_max_threads();
+#endif
+    const int F = N + 1;
+    enum { CH = 2048 };
+    double* gpart = malloc(sizeof(double) * (size_t)T * F);
+    double* fpart = malloc(sizeof(double) * T);
+    double* mpart = malloc(sizeof(double) * T);
+    for (int q = 0; q < n_nodes; ++q) {
+        const int u = nodes[q];
+        const double* xu = x + (size_t)q * F;
+        const int8_t* su = spins + (int64_t)u * ld;
+        /* logRISE: shift by the largest exponent (same value of f, no overflow) */
+        double tmax = 0.0;
+        for (int t = 0; t < T; ++t) { mpart[t] = -INFINITY; fpart[t] = 0.0; }
+        memset(gpart, 0, sizeof(double) * (size_t)T * F);
+        if (form == FORM_LOGRISE) {
+#pragma omp parallel num_threads(T)
+            {
+                int t = 0;
+#ifdef _OPENMP
+                t = omp_get_thread_num();
+#endif
+                double* e = malloc(sizeof(double) * CH);
+                double mx = -INFINITY;
+                int nt = 1;
+#ifdef _OPENMP
+                nt = omp_get_num_threads();
+#endif
+                const int64_t k0 = K * t / nt, k1 = K * (t + 1) / nt;
+                for (int64_t c0 = k0; c0 < k1; c0 += CH) {
+                    const int n = (int)((k1 - c0) < CH ? (k1 - c0) : CH);
+                    for (int k = 0; k < n; ++k) e[k] = xu[N];
+                    for (int i = 0; i < N; ++i) {
+                        if (i == u || xu[i] == 0.0) continue;
+                        const int8_t* si = spins + (int64_t)i * ld + c0;
+                        const double xi = xu[i];
+                        for (int k = 0; k < n; ++k) e[k] += xi * si[k];
+                    }
+                    for (int k = 0; k < n; ++k) { const double t_k = su[c0 + k] * e[k]; if (-t_k > mx) mx = -t_k; }
+                }
+                mpart[t] = mx;
+                free(e);
+            }
+            tmax = -INFINITY;
+            for (int t = 0; t < T; ++t) if (mpart[t] > tmax) tmax = mpart[t];     /* slots of threads not granted hold -inf */
+        }
+#pragma omp parallel num_threads(T)
+        {
+            int t = 0;
+#ifdef _OPENMP
+            t = omp_get_thread_num();
+#endif
+            double* e = malloc(sizeof(double) * CH);
+            double* r = malloc(sizeof(double) * CH);
+            double* g = gpart + (size_t)t * F;
+            memset(g, 0, sizeof(double) * F);
+            double acc = 0.0;
+            int nt = 1;
+#ifdef _OPENMP
+            nt = omp_get_num_threads();
+#endif
+            const int64_t k0 = K * t / nt, k1 = K * (t + 1) / nt;
+            for (int64_t c0 = k0; c0 < k1; c0 += CH) {
+                const int n = (int)((k1 - c0) < CH ? (k1 - c0) : CH);
+                for (int k = 0; k < n; ++k) e[k] = xu[N];
+                for (int i = 0; i < N; ++i) {
+                    if (i == u || xu[i] == 0.0) continue;
+                    const int8_t* si = spins + (int64_t)i * ld + c0;
+                    const double xi = xu[i];
+                    for (int k = 0; k < n; ++k) e[k] += xi * si[k];
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double s = su[c0 + k], t_k = s * e[k], w = counts[c0 + k] / M;
+                    double gw;
+                    if (form == FORM_RISE) { gw = w * exp(-t_k); acc += gw; }
+                    else if (form == FORM_LOGRISE) { gw = w * exp(-t_k - tmax); acc += gw; }
+                    else {
+                        const double a = -2.0 * t_k;
+                        acc += w * ((a > 0 ? a : 0.0) + log1p(exp(-fabs(a))));
+                        gw = 2.0 * w * 0.5 * (1.0 - tanh(t_k));
+                    }
+                    r[k] = -gw * s;                       /* d f / d (sum_i x_i s_i + h) for this row */
+                }
+                if (g_out) {
+                    for (int i = 0; i < N; ++i) {
+                        const int8_t* si = spins + (int64_t)i * ld + c0;
+                        double d = 0.0;
+                        for (int k = 0; k < n; ++k) d += r[k] * si[k];
+                        g[i] += d;
+                    }
+                    double d = 0.0;
+                    for (int k = 0; k < n; ++k) d += r[k];
+                    g[N] += d;
+                }
+            }
+            fpart[t] = acc;
+            free(e); free(r);
+        }
+        double acc = 0.0;
+        for (int t = 0; t < T; ++t) acc += fpart[t];
+        f_out[q] = (form == FORM_LOGRISE) ? log(acc) + tmax : acc;
+        if (g_out) {
+            double* go = g_out + (size_t)q * F;
+            for (int f = 0; f < F; ++f) {
+                double v = 0.0;
+                for (int t = 0; t < T; ++t) v += gpart[(size_t)t * F + f];
+                go[f] = (form == FORM_LOGRISE) ? v / acc : v;
+            }
+            go[u] = 0.0;
+        }
+    }
+    free(gpart); free(fpart); free(mpart);
     return 0;
 }
 

@@ -77,3 +77,64 @@ def test_two_rank_gather_matches_oracle():
     for rank, err, shape in results:
         assert shape == (7, 7)
         assert err <= 1e-12
+
+
+def test_sample_slices_cover_all_rows():
+    sys.path.insert(0, str(ROOT))
+    import gml_b200  # noqa: F401
+    from gml_b200.distributed import sample_slice
+    for k in (1, 255, 256, 30_001, 10_000_000):
+        for world in (1, 2, 3, 8):
+            cuts = [sample_slice(k, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == k
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            assert all(b % 256 == 0 or b == k for b, _ in cuts)
+
+
+def _slice_worker(rank, world, port, counts, spins, x, result_q):
+    for p in (ROOT, ROOT / "oracle"):
+        sys.path.insert(0, str(p))
+    import c_oracle as c
+    import gml_b200  # noqa: F401
+    from gml_b200.distributed import sample_slice
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b, e = sample_slice(spins.shape[1], world, rank)
+    # what a rank of the sample-sharded mode holds: its rows, weights c_k / M_global (comm_globalize_histogram), and per
+    # pass the un-normalised partial sums of f and of the gradient, combined with ONE all-reduce (csrc/comm.cu)
+    m_local = torch.tensor([counts[b:e].sum()], dtype=torch.float64)
+    m_global = m_local.clone()
+    dist.all_reduce(m_global)
+    f, g = c.eval_pairwise(counts[b:e], np.ascontiguousarray(spins[:, b:e]), "RISE", x)
+    scale = float(m_local / m_global)
+    part = torch.from_numpy(np.concatenate([f[:, None], g], axis=1) * scale)
+    dist.all_reduce(part)
+    result_q.put((rank, part.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sample_sharded_sums_match_oracle():
+    """Host logic of the sample-sharded partition on CPU (gloo, world 2): slices + global weights + one all-reduce of the
+    partial (f, grad f) sums reproduce the full-histogram evaluation of the oracle, identically on both ranks."""
+    for p in (ROOT, ROOT / "oracle"):
+        sys.path.insert(0, str(p))
+    import c_oracle as c
+    rng = np.random.default_rng(2)
+    n, k = 9, 1000
+    spins = rng.choice(np.array([-1, 1], dtype=np.int8), size=(n, k))
+    counts = rng.integers(1, 4, size=k).astype(np.float64)
+    x = rng.normal(size=(n, n + 1)) * 0.2
+    f, g = c.eval_pairwise(counts, spins, "RISE", x)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_slice_worker, args=(r, 2, port, counts, spins, x, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(results[0][1], results[1][1])
+    assert np.abs(results[0][1][:, 0] - f).max() <= 1e-13 and np.abs(results[0][1][:, 1:] - g).max() <= 1e-13

@@ -67,3 +67,47 @@ def test_objective_known_answers(golden):
     for form, want in (("RISE", 0.969954153785), ("logRISE", -0.030242641570), ("RPLE", 0.663177462752)):
         _, info = c.learn_pairwise(s, form, return_info=True)
         assert abs(info["objective"][0] - want) <= 1e-9
+
+
+@pytest.mark.parametrize("form", FORMS)
+def test_c_eval_pairwise_matches_smooth_parts(form):
+    """The histogram-sweeping f / grad f entry (gml_oracle_eval_pairwise) is the same function as the per-node
+    float64 restatement smooth_parts over nodal_stat (src/GraphicalModelLearning.jl:162, 170/279/317)."""
+    rng = np.random.default_rng(11)
+    n, k = 23, 5003
+    spins = rng.choice(np.array([-1, 1], dtype=np.int8), size=(n, k))
+    counts = rng.integers(1, 6, size=k).astype(np.float64)
+    hist = np.concatenate([counts[:, None], spins.T.astype(np.float64)], axis=1)
+    w = counts / counts.sum()
+    x = rng.normal(size=(n, n + 1)) * 0.2 * (rng.random((n, n + 1)) < 0.4)
+    nodes = np.array([0, 7, 22, 13], dtype=np.int32)
+    f, g = c.eval_pairwise(counts, spins, form, x[nodes], nodes)
+    for q, u in enumerate(nodes):
+        stat = o.nodal_stat_pairwise(hist, u)
+        xv = x[u, :n].copy(); xv[u] = x[u, n]
+        fu, gu, _ = o.smooth_parts(form, xv, stat, w, hess=False)
+        gr = np.zeros(n + 1); gr[:n] = gu; gr[n] = gu[u]; gr[u] = 0.0
+        assert abs(f[q] - fu) <= 1e-13 * max(1.0, abs(fu))
+        assert np.abs(g[q] - gr).max() <= 1e-13
+    f2, _ = c.eval_pairwise(counts, spins, form, x[nodes], nodes, want_grad=False)
+    assert np.array_equal(f, f2)
+
+
+def test_c_oracle_inner_threads_and_node_ranges():
+    """Few nodes of a larger problem use the host threads inside the Hessian accumulation: same answer as the
+    node-parallel solve; learn_multibody(nodes=...) returns the rows of the full solve."""
+    rng = np.random.default_rng(5)
+    n, k = 12, 20000
+    spins = rng.choice(np.array([-1, 1], dtype=np.int8), size=(n, k))
+    spins[3] = spins[2] * np.where(rng.random(k) < 0.8, 1, -1).astype(np.int8)
+    counts = np.ones(k)
+    c.set_threads(4)
+    lam = 0.01
+    full = c.learn_pairwise_packed(counts, spins, "RISE", lam, False)
+    part = c.learn_pairwise_packed(counts, spins, "RISE", lam, False, nodes=(2, 4))     # 2 nodes x 2 inner threads
+    assert np.abs(part[2:4] - full[2:4]).max() <= 1e-11
+    hist = np.concatenate([counts[:, None], spins.T.astype(np.float64)], axis=1)[:4000, :7]
+    a = c.learn_multibody(hist, 0.3, False, 3)
+    b = c.learn_multibody(hist, 0.3, False, 3, nodes=(1, 3))
+    assert set(b) == {k_ for k_ in a if k_[0] in (2, 3)}
+    assert max(abs(a[k_] - b[k_]) for k_ in b) <= 1e-11
