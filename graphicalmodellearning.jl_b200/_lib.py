@@ -19,6 +19,7 @@ SOLVER_AUTO, SOLVER_NEWTON, SOLVER_FISTA_CC, SOLVER_FISTA_TC = 0, 1, 2, 3
 EXPORTS = (
     "gml_b200_version", "gml_b200_last_error", "gml_b200_device_count", "gml_b200_opts_default",
     "gml_b200_learn_pairwise", "gml_b200_learn_multibody", "gml_b200_multibody_num_keys",
+    "gml_b200_learn_pairwise_matrix", "gml_b200_learn_multibody_matrix", "gml_b200_upload_matrix",
     "gml_b200_create", "gml_b200_destroy", "gml_b200_upload_histogram",
     "gml_b200_attach_histogram_device", "gml_b200_num_samples", "gml_b200_solve_pairwise",
     "gml_b200_solve_pairwise_device", "gml_b200_solve_pairwise_path", "gml_b200_solve_multibody", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
@@ -83,6 +84,11 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
                                             c.c_int32, op, vp, vp, sp]
     lib.gml_b200_learn_multibody.argtypes = [vp, vp, c.c_int64, c.c_int32, c.c_int64, c.c_int32, c.c_double,
                                              op, vp, vp, sp]
+    lib.gml_b200_learn_pairwise_matrix.argtypes = [vp, c.c_int32, c.c_int64, c.c_int32, c.c_int64, c.c_int32, c.c_double,
+                                                   c.c_int32, op, vp, vp, sp]
+    lib.gml_b200_learn_multibody_matrix.argtypes = [vp, c.c_int32, c.c_int64, c.c_int32, c.c_int64, c.c_int32, c.c_double,
+                                                    op, vp, vp, sp]
+    lib.gml_b200_upload_matrix.argtypes = [vp, vp, c.c_int32, c.c_int64, c.c_int64, c.c_int32, c.c_int64, sp]
     lib.gml_b200_multibody_num_keys.argtypes = [c.c_int32, c.c_int32]
     lib.gml_b200_multibody_num_keys.restype = c.c_int64
     lib.gml_b200_create.argtypes = [c.POINTER(vp), c.c_int32]

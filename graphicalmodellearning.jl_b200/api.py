@@ -235,16 +235,7 @@ def learn_packed(counts: np.ndarray, spins: np.ndarray, formulation: GMLFormulat
                                           ctypes.byref(opts), _ptr(vals), _ptr(obj), ctypes.byref(stats))
         method.last_stats = stats.as_dict()
         _lib.check(rc)
-        recon = {}
-        for u in range(1, N + 1):
-            for f, key in enumerate(multirise_keys(N, u, order)):
-                recon[key] = float(vals[u - 1, f])                      # :129-132
-        if formulation.symmetrization:                                   # :135-149
-            groups: Dict[Tuple[int, ...], list] = {}
-            for k, v in recon.items():
-                groups.setdefault(tuple(sorted(k)), []).append(v)
-            recon = {k: float(np.mean(v)) for k, v in groups.items()}
-        result = FactorGraph(order, N, "spin", recon)                    # :151
+        result = _multirise_result(vals, N, formulation)
     else:
         form_id = {RISE: 0, logRISE: 1, RPLE: 2}.get(type(formulation))
         if form_id is None:
@@ -261,6 +252,65 @@ def learn_packed(counts: np.ndarray, spins: np.ndarray, formulation: GMLFormulat
     return result
 
 
+MATRIX_DTYPES = {np.dtype(np.float64): 0, np.dtype(np.int64): 1, np.dtype(np.float32): 2, np.dtype(np.int32): 3,
+                 np.dtype(np.int8): 4}
+
+
+def _multirise_result(vals: np.ndarray, N: int, formulation) -> "FactorGraph":
+    order = int(formulation.interaction_order)
+    recon = {}
+    for u in range(1, N + 1):
+        for f, key in enumerate(multirise_keys(N, u, order)):
+            recon[key] = float(vals[u - 1, f])                      # :129-132
+    if formulation.symmetrization:                                   # :135-149
+        groups: Dict[Tuple[int, ...], list] = {}
+        for k, v in recon.items():
+            groups.setdefault(tuple(sorted(k)), []).append(v)
+        recon = {k: float(np.mean(v)) for k, v in groups.items()}
+    return FactorGraph(order, N, "spin", recon)                      # :151
+
+
+def learn_matrix(samples: np.ndarray, formulation: GMLFormulation, method: B200, return_info: bool = False):
+    """learn() straight from the reference's input type: a COLUMN-major (Fortran-order, i.e. Julia-native) K x (N+1) matrix
+    [count, s_1..s_N] of float64 / int64 / float32 / int32 / int8.  The library narrows the spins on the host while it
+    streams them to the device and computes num_samples and lambda itself (src/GraphicalModelLearning.jl:76-81, :157)."""
+    lib = _lib.load()
+    if samples.ndim != 2 or samples.shape[1] < 2 or samples.shape[0] < 1:
+        raise ValueError("samples must be a K x (N+1) matrix [count, s_1..s_N]")
+    K, N = samples.shape[0], samples.shape[1] - 1
+    col_major = samples.strides[0] == samples.itemsize and samples.strides[1] >= K * samples.itemsize and \
+        samples.strides[1] % samples.itemsize == 0
+    if not col_major or samples.dtype not in MATRIX_DTYPES:
+        raise ValueError("learn_matrix needs a column-major (Fortran-ordered) matrix of float64 / int64 / float32 / int32 / int8")
+    ld = samples.strides[1] // samples.itemsize          # leading dimension >= K (a row range of a taller matrix is fine)
+    stats = _lib.Stats()
+    obj = np.zeros(N)
+    opts = method._opts()
+    dt = MATRIX_DTYPES[samples.dtype]
+    if isinstance(formulation, multiRISE):
+        order = int(formulation.interaction_order)
+        vals = np.zeros((N, int(lib.gml_b200_multibody_num_keys(N, order))))
+        rc = lib.gml_b200_learn_multibody_matrix(_ptr(samples), dt, K, N, ld, order, float(formulation.regularizer),
+                                                 ctypes.byref(opts), _ptr(vals), _ptr(obj), ctypes.byref(stats))
+        method.last_stats = stats.as_dict()
+        _lib.check(rc)
+        result = _multirise_result(vals, N, formulation)
+    else:
+        form_id = {RISE: 0, logRISE: 1, RPLE: 2}.get(type(formulation))
+        if form_id is None:
+            raise NotImplementedError(f"{type(formulation).__name__} is not on the B200 hot path")
+        theta = np.zeros((N, N), order="F")
+        rc = lib.gml_b200_learn_pairwise_matrix(_ptr(samples), dt, K, N, ld, form_id, float(formulation.regularizer),
+                                                int(bool(formulation.symmetrization)), ctypes.byref(opts), _ptr(theta),
+                                                _ptr(obj), ctypes.byref(stats))
+        method.last_stats = stats.as_dict()
+        _lib.check(rc)
+        result = np.ascontiguousarray(theta)
+    if return_info:
+        return result, {"objective": obj, **method.last_stats}
+    return result
+
+
 def learn(samples, formulation: Optional[GMLFormulation] = None, method: Optional[GMLMethod] = None,
           return_info: bool = False):
     """learn(samples[, formulation[, method]]) -- src/GraphicalModelLearning.jl:69-73.
@@ -274,6 +324,9 @@ def learn(samples, formulation: Optional[GMLFormulation] = None, method: Optiona
                                   "pass B200() as the method")
     if not isinstance(method, B200):
         raise TypeError("method must be a GMLMethod")
+    samples = np.asarray(samples)
+    if samples.ndim == 2 and samples.flags.f_contiguous and samples.dtype in MATRIX_DTYPES and samples.shape[0] > 1:
+        return learn_matrix(samples, formulation, method, return_info=return_info)      # Julia-native layout: no host copy
     counts, spins = pack_histogram(samples)
     return learn_packed(counts, spins, formulation, method, return_info=return_info)
 

@@ -440,6 +440,32 @@ int gml_b200_upload_histogram(gml_b200_handle* h, const double* counts, const in
     });
 }
 
+int gml_b200_upload_matrix(gml_b200_handle* h, const void* samples, int32_t dtype, int64_t row_begin, int64_t K, int32_t N,
+                           int64_t ld, gml_b200_stats* stats) {
+    return guarded([&] {
+        GML_REQUIRE(h && samples, "null argument");
+        GML_REQUIRE(K >= 1 && N >= 1 && row_begin >= 0 && ld >= row_begin + K, "samples matrix needs K >= 1, N >= 1, ld >= row_begin + K");
+        const double t0 = now_ms();
+        GML_CUDA(cudaSetDevice(h->device));
+        DevBuf<double> dc;
+        dc.alloc(K);
+        Histogram& hist = h->hist;
+        const int64_t Kp = round_up(K, KPAD);
+        h->has_hist = false;
+        hist.base.alloc((size_t)round_up(N + 1, FPAD) * Kp);
+        double host_ms = 0.0;
+        ingest_matrix(samples, dtype, ld, row_begin, K, N, hist.base.p, Kp, dc.p, 0, &host_ms);
+        gml_b200_stats tmp;
+        const int rc = gml_b200_attach_histogram_device(h, dc.p, hist.base.p, K, N, Kp, &tmp);     // validate + pad in place
+        if (rc != GML_B200_OK) throw CudaError{rc};
+        if (stats) {
+            *stats = tmp;
+            stats->h2d_ms = host_ms;
+            stats->total_ms = now_ms() - t0;
+        }
+    });
+}
+
 int gml_b200_solve_pairwise_device(gml_b200_handle* h, int32_t formulation, double lambda, const gml_b200_opts* opts,
                                    double* d_out_rows, double* d_out_objective, gml_b200_stats* stats) {
     return guarded([&] {
@@ -768,7 +794,22 @@ static int learn_pairwise_multi_device(const double* counts, const int8_t* spins
 // rows (one pass over the host link per byte, no replication), the threads join one NCCL communicator and advance all
 // node problems in lockstep (all-reduce of the exact int64 gradient sums per pass, csrc/comm.cu).  Every device ends
 // with the full solution; device `base.device` symmetrises it on the device (:184-186) and writes the caller's matrix.
-static int learn_pairwise_multi_device_samples(const double* counts, const int8_t* spins, int64_t K, int32_t N, int64_t ld,
+// where the histogram comes from: packed (counts + int8 spins) or the reference's K x (N+1) matrix
+struct HostSource {
+    const double* counts = nullptr; const int8_t* spins = nullptr;     // packed form
+    const void* matrix = nullptr; int dtype = 0;                       // matrix form
+    int64_t ld = 0;
+    double regularizer = -1.0;      // >= 0: lambda = regularizer*sqrt(log(N^2/0.05)/M) (:157) from the global sample count
+    int upload(gml_b200_handle* h, int64_t k0, int64_t k1, int32_t N, gml_b200_stats* up) const {
+        if (matrix) return gml_b200_upload_matrix(h, matrix, dtype, k0, k1 - k0, N, ld, up);
+        return gml_b200_upload_histogram(h, counts + k0, spins + k0, k1 - k0, N, ld, up);
+    }
+    double lambda_for(double lambda, int32_t N, double M) const {
+        return regularizer >= 0.0 ? regularizer * std::sqrt(std::log(((double)N * (double)N) / 0.05) / M) : lambda;
+    }
+};
+
+static int learn_pairwise_multi_device_samples(const HostSource& src, int64_t K, int32_t N,
                                                int32_t formulation, double lambda, int32_t symmetrize, const gml_b200_opts& base,
                                                int n_dev, double* out_theta, double* out_objective, gml_b200_stats* stats) {
     const double t0 = now_ms();
@@ -790,7 +831,7 @@ static int learn_pairwise_multi_device_samples(const double* counts, const int8_
             std::memset(&sts[r], 0, sizeof(gml_b200_stats));
             gml_b200_stats up{};
             int rc = gml_b200_create(&h, o.device);
-            if (rc == GML_B200_OK) rc = gml_b200_upload_histogram(h, counts + k0, spins + k0, k1 - k0, N, ld, &up);
+            if (rc == GML_B200_OK) rc = src.upload(h, k0, k1, N, &up);
             // every thread must reach the communicator set-up, also after a failed upload (the others would wait for ever)
             const int rc_comm = h ? gml_b200_comm_init(h, ident, r, n_dev) : GML_B200_ECUDA;
             if (rc == GML_B200_OK) rc = rc_comm;
@@ -802,11 +843,12 @@ static int learn_pairwise_multi_device_samples(const double* counts, const int8_
             }
             if (rc == GML_B200_OK) rc = gml_b200_comm_globalize_histogram(h);
             if (rc == GML_B200_OK) {
-                if (r == 0) rc = gml_b200_solve_pairwise(h, formulation, lambda, symmetrize, &o, out_theta, out_objective, &sts[r]);
+                const double lam = src.lambda_for(lambda, N, gml_b200_num_samples(h));     // global M after the globalize step
+                if (r == 0) rc = gml_b200_solve_pairwise(h, formulation, lam, symmetrize, &o, out_theta, out_objective, &sts[r]);
                 else {
                     DevBuf<double> rows;
                     try { rows.alloc((size_t)N * N); } catch (const CudaError& e) { rc = e.code; }
-                    if (rc == GML_B200_OK) rc = gml_b200_solve_pairwise_device(h, formulation, lambda, &o, rows.p, nullptr, &sts[r]);
+                    if (rc == GML_B200_OK) rc = gml_b200_solve_pairwise_device(h, formulation, lam, &o, rows.p, nullptr, &sts[r]);
                     cudaStreamSynchronize(h->own_stream);
                 }
                 sts[r].pack_ms = up.pack_ms; sts[r].h2d_ms = up.h2d_ms; sts[r].kernel_launches += up.kernel_launches;
@@ -843,7 +885,9 @@ int gml_b200_learn_pairwise(const double* counts, const int8_t* spins, int64_t K
         // opts->reserved[2] = 2 forces node shards.
         const bool tc = (opts->solver == GML_B200_SOLVER_AUTO && N + 1 > NEWTON_MAX_F) || opts->solver == GML_B200_SOLVER_FISTA_TC;
         if (n_dev > 1 && tc && opts->reserved[2] != 2 && K / n_dev >= 65536 && opts->barrier_mu == 0.0) {
-            const int rc = learn_pairwise_multi_device_samples(counts, spins, K, N, ld, formulation, lambda, symmetrize, *opts,
+            HostSource src;
+            src.counts = counts; src.spins = spins; src.ld = ld;
+            const int rc = learn_pairwise_multi_device_samples(src, K, N, formulation, lambda, symmetrize, *opts,
                                                                n_dev, out_theta, out_objective, stats);
             if (rc >= 0) return rc;
         }
@@ -876,6 +920,65 @@ int gml_b200_learn_multibody(const double* counts, const int8_t* spins, int64_t 
     gml_b200_stats up{}, so{};
     rc = gml_b200_upload_histogram(h, counts, spins, K, N, ld, &up);
     if (rc == GML_B200_OK) rc = gml_b200_solve_multibody(h, order, lambda, opts, out_vals, out_objective, &so);
+    if (stats) {
+        *stats = so;
+        stats->pack_ms = up.pack_ms; stats->h2d_ms = up.h2d_ms;
+        stats->kernel_launches += up.kernel_launches;
+        stats->total_ms += up.total_ms;
+    }
+    gml_b200_destroy(h);
+    return rc;
+}
+
+int gml_b200_learn_pairwise_matrix(const void* samples, int32_t dtype, int64_t K, int32_t N, int64_t ld,
+                                   int32_t formulation, double regularizer, int32_t symmetrize, const gml_b200_opts* opts,
+                                   double* out_theta, double* out_objective, gml_b200_stats* stats) {
+    if (!(regularizer >= 0.0) || !std::isfinite(regularizer)) { set_error("regularizer must be finite and >= 0"); return GML_B200_EINVAL; }
+    HostSource src;
+    src.matrix = samples; src.dtype = dtype; src.ld = ld; src.regularizer = regularizer;
+    if (opts && opts->reserved[4] > 1) {
+        const int n_dev = std::min<int>(opts->reserved[4], std::max(1, gml_b200_device_count() - opts->device));
+        const bool tc = (opts->solver == GML_B200_SOLVER_AUTO && N + 1 > NEWTON_MAX_F) || opts->solver == GML_B200_SOLVER_FISTA_TC;
+        if (n_dev > 1 && tc && K / n_dev >= 65536 && opts->barrier_mu == 0.0) {
+            const int rc = learn_pairwise_multi_device_samples(src, K, N, formulation, 0.0, symmetrize, *opts, n_dev, out_theta,
+                                                               out_objective, stats);
+            if (rc >= 0) return rc;
+        }
+    }
+    gml_b200_handle* h = nullptr;
+    int rc = gml_b200_create(&h, opts ? opts->device : 0);
+    if (rc != GML_B200_OK) return rc;
+    gml_b200_stats up{}, so{};
+    rc = src.upload(h, 0, K, N, &up);
+    if (rc == GML_B200_OK) {
+        gml_b200_opts o; fill_opts(o, opts);
+        o.reserved[4] = 0;
+        rc = gml_b200_solve_pairwise(h, formulation, src.lambda_for(0.0, N, gml_b200_num_samples(h)), symmetrize, &o, out_theta,
+                                     out_objective, &so);
+    }
+    if (stats) {
+        *stats = so;
+        stats->pack_ms = up.pack_ms; stats->h2d_ms = up.h2d_ms;
+        stats->kernel_launches += up.kernel_launches;
+        stats->total_ms += up.total_ms;
+    }
+    gml_b200_destroy(h);
+    return rc;
+}
+
+int gml_b200_learn_multibody_matrix(const void* samples, int32_t dtype, int64_t K, int32_t N, int64_t ld, int32_t order,
+                                    double regularizer, const gml_b200_opts* opts, double* out_vals, double* out_objective,
+                                    gml_b200_stats* stats) {
+    if (!(regularizer >= 0.0) || !std::isfinite(regularizer)) { set_error("regularizer must be finite and >= 0"); return GML_B200_EINVAL; }
+    HostSource src;
+    src.matrix = samples; src.dtype = dtype; src.ld = ld; src.regularizer = regularizer;
+    gml_b200_handle* h = nullptr;
+    int rc = gml_b200_create(&h, opts ? opts->device : 0);
+    if (rc != GML_B200_OK) return rc;
+    gml_b200_stats up{}, so{};
+    rc = src.upload(h, 0, K, N, &up);
+    if (rc == GML_B200_OK)
+        rc = gml_b200_solve_multibody(h, order, src.lambda_for(0.0, N, gml_b200_num_samples(h)), opts, out_vals, out_objective, &so);
     if (stats) {
         *stats = so;
         stats->pack_ms = up.pack_ms; stats->h2d_ms = up.h2d_ms;

@@ -142,6 +142,10 @@ const int8_t* ensure_Qb(Histogram& h, const int8_t* Q, int Fp, cudaStream_t st);
 double subsample_weight(const Histogram& h, int64_t stride, cudaStream_t st);
 void launch_block_copy(const int8_t* Q, int8_t* Qb, int Fp, int64_t Kp, cudaStream_t st);
 
+// --- ingest.cu : K x (N+1) matrix of Real (the reference's `samples`) -> device rows, narrowed on the host by a thread pool
+void ingest_matrix(const void* samples, int dtype, int64_t ld, int64_t k0, int64_t K, int32_t N, int8_t* d_base, int64_t Kp,
+                   double* d_counts, int n_threads, double* out_host_ms);
+
 // --- newton.cu : fp64 proximal-Newton / barrier-Newton for small feature counts
 constexpr int NEWTON_MAX_F = 64;
 void solve_newton(const NodeProblem& p, const gml_b200_opts& o, SolveResult& r, cudaStream_t st);

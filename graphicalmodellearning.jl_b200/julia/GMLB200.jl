@@ -53,8 +53,9 @@ end
 Batched GPU method.  `tol`: stopping tolerance (max-norm of the proximal-gradient mapping for the
 FISTA solvers, Newton step for the small-problem solver; 0 selects 1e-6 / 1e-12).  `barrier_mu > 0`
 returns the log-barrier point Ipopt stops at instead of the exact L1 minimiser (1e-9 reproduces the
-stored test fixtures to ~1e-9; available for problems with at most 64 features per node).  `devices > 1` shards
-the node problems over that many GPUs (device, device+1, ...) from this one Julia process.
+stored test fixtures to ~1e-9; available for problems with at most 64 features per node).  `devices > 1` splits
+the work over that many GPUs (device, device+1, ...) from this one Julia process: histogram rows when every device keeps
+at least 65536 of them (sample-sharded solve, NCCL all-reduce per pass), node shards otherwise.
 """
 mutable struct B200 <: GMLMethod
     tol::Float64
@@ -84,26 +85,25 @@ function _gml_b200_check(rc::Integer)
     error("gml_b200 error $(rc): $(msg)")
 end
 
-# [count, s_1..s_N] -> counts::Vector{Float64}, spins::Matrix{Int8} (K x N, column-major = spin-major)
-function _gml_b200_pack(samples::Array{T,2}) where T <: Real
-    counts = Float64.(samples[:, 1])
-    spins = Int8.(samples[:, 2:end])      # InexactError on anything that is not an integer in Int8 range
-    return counts, spins
-end
+# element types the library ingests directly from the reference's K x (N+1) `samples` matrix (include/gml_b200.h:
+# GML_B200_DTYPE_*); any other Real is converted to Float64 first
+const _gml_b200_dtype = Dict(Float64 => 0, Int64 => 1, Float32 => 2, Int32 => 3, Int8 => 4)
+_gml_b200_native(samples::Array{T,2}) where T <: Real = haskey(_gml_b200_dtype, T) ? samples : Float64.(samples)
 
 function _gml_b200_pairwise(samples::Array{T,2}, formulation_id::Integer, regularizer::Real,
                             symmetrization::Bool, method::B200) where T <: Real
-    num_conf, num_spins, num_samples = data_info(samples)                                   # :76-81
-    lambda = regularizer*sqrt(log((num_spins^2)/0.05)/num_samples)                          # :157
-    counts, spins = _gml_b200_pack(samples)
+    # `samples` goes to the library AS IS (column-major, ld = num_conf): data_info (:76-81), lambda (:157), the narrowing of
+    # the spins to bytes (threaded, validated) and the transfer all happen inside the call
+    native = _gml_b200_native(samples)
+    num_conf, num_spins = size(native, 1), size(native, 2) - 1
     reconstruction = Array{Float64}(undef, num_spins, num_spins)                            # :159
     opts = _gml_b200_opts(method)
-    GC.@preserve counts spins reconstruction begin
-        rc = ccall((:gml_b200_learn_pairwise, _libgml_b200), Cint,
-                   (Ptr{Cdouble}, Ptr{Int8}, Int64, Int32, Int64, Int32, Cdouble, Int32,
+    GC.@preserve native reconstruction begin
+        rc = ccall((:gml_b200_learn_pairwise_matrix, _libgml_b200), Cint,
+                   (Ptr{Cvoid}, Int32, Int64, Int32, Int64, Int32, Cdouble, Int32,
                     Ref{_GMLB200Opts}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{GMLB200Stats}),
-                   counts, spins, num_conf, num_spins, num_conf, formulation_id, lambda,
-                   symmetrization ? 1 : 0, opts, reconstruction, C_NULL, method.stats)
+                   native, _gml_b200_dtype[eltype(native)], num_conf, num_spins, num_conf, formulation_id,
+                   Float64(regularizer), symmetrization ? 1 : 0, opts, reconstruction, C_NULL, method.stats)
     end
     _gml_b200_check(rc)
     return reconstruction          # column-major N x N, row u = node u, diagonal = fields (:181-188)
@@ -117,19 +117,18 @@ learn(samples::Array{T,2}, formulation::RPLE, method::B200) where T <: Real =
     _gml_b200_pairwise(samples, 2, formulation.regularizer, formulation.symmetrization, method)
 
 function learn(samples::Array{T,2}, formulation::multiRISE, method::B200) where T <: Real
-    num_conf, num_spins, num_samples = data_info(samples)
-    lambda = formulation.regularizer*sqrt(log((num_spins^2)/0.05)/num_samples)              # :86
+    native = _gml_b200_native(samples)
+    num_conf, num_spins = size(native, 1), size(native, 2) - 1
     inter_order = formulation.interaction_order
-    counts, spins = _gml_b200_pack(samples)
     n_keys = ccall((:gml_b200_multibody_num_keys, _libgml_b200), Int64, (Int32, Int32), num_spins, inter_order)
     vals = Array{Float64}(undef, n_keys, num_spins)      # vals[f, u] == out_vals[u*n_keys + f] of the C side
     opts = _gml_b200_opts(method)
-    GC.@preserve counts spins vals begin
-        rc = ccall((:gml_b200_learn_multibody, _libgml_b200), Cint,
-                   (Ptr{Cdouble}, Ptr{Int8}, Int64, Int32, Int64, Int32, Cdouble,
+    GC.@preserve native vals begin
+        rc = ccall((:gml_b200_learn_multibody_matrix, _libgml_b200), Cint,
+                   (Ptr{Cvoid}, Int32, Int64, Int32, Int64, Int32, Cdouble,
                     Ref{_GMLB200Opts}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{GMLB200Stats}),
-                   counts, spins, num_conf, num_spins, num_conf, inter_order, lambda,
-                   opts, vals, C_NULL, method.stats)
+                   native, _gml_b200_dtype[eltype(native)], num_conf, num_spins, num_conf, inter_order,
+                   Float64(formulation.regularizer), opts, vals, C_NULL, method.stats)      # lambda of :86 inside
     end
     _gml_b200_check(rc)
 

@@ -121,6 +121,26 @@ int gml_b200_learn_multibody(const double* counts, const int8_t* spins, int64_t 
 
 int64_t gml_b200_multibody_num_keys(int32_t N, int32_t interaction_order);
 
+/* ---- the reference's own input type ---------------------------------------------------------------
+ * `samples` as learn() receives it (src/GraphicalModelLearning.jl:69-81): a COLUMN-major K x (N+1) matrix with leading
+ * dimension ld (in elements), column 0 = counts, column 1+i = spin i in {-1,+1}; element type Float64 (readdlm) or Int64
+ * (`sample`, src/sampling.jl:54), also Float32 / Int32 / Int8.  The library narrows the spins to bytes on the host with a
+ * thread pool (validating +-1) while streaming them to the device, computes num_samples (:79) and
+ * lambda = regularizer*sqrt(log(N^2/0.05)/num_samples) (:157) itself, and then does what gml_b200_learn_pairwise does.
+ * With opts->reserved[4] = n > 1 the histogram rows are split over n devices (sample-sharded solve). */
+#define GML_B200_DTYPE_F64 0
+#define GML_B200_DTYPE_I64 1
+#define GML_B200_DTYPE_F32 2
+#define GML_B200_DTYPE_I32 3
+#define GML_B200_DTYPE_I8 4
+int gml_b200_learn_pairwise_matrix(const void* samples, int32_t dtype, int64_t K, int32_t N, int64_t ld,
+                                   int32_t formulation, double regularizer, int32_t symmetrize,
+                                   const gml_b200_opts* opts, double* out_theta, double* out_objective /* N, nullable */,
+                                   gml_b200_stats* stats /* nullable */);
+int gml_b200_learn_multibody_matrix(const void* samples, int32_t dtype, int64_t K, int32_t N, int64_t ld,
+                                    int32_t interaction_order, double regularizer, const gml_b200_opts* opts,
+                                    double* out_vals, double* out_objective /* N, nullable */, gml_b200_stats* stats);
+
 /* ---- handle API: keep the histogram resident in HBM across solves ----------------------------- */
 
 int gml_b200_create(gml_b200_handle** h, int32_t device);
@@ -129,6 +149,10 @@ void gml_b200_destroy(gml_b200_handle* h);
 /* data_info (src/GraphicalModelLearning.jl:76-81) + device layout build.  Host pointers. */
 int gml_b200_upload_histogram(gml_b200_handle* h, const double* counts, const int8_t* spins,
                               int64_t K, int32_t N, int64_t ld, gml_b200_stats* stats);
+/* Same from the reference's K x (N+1) matrix (see gml_b200_learn_pairwise_matrix); rows [row_begin, row_begin + K) of a
+ * matrix with leading dimension ld are ingested.  stats->h2d_ms covers narrowing + transfer (they overlap). */
+int gml_b200_upload_matrix(gml_b200_handle* h, const void* samples, int32_t dtype, int64_t row_begin, int64_t K, int32_t N,
+                           int64_t ld, gml_b200_stats* stats);
 /* Same, but counts/spins already live in device memory of h's device (no host copies). */
 int gml_b200_attach_histogram_device(gml_b200_handle* h, const double* d_counts, const int8_t* d_spins,
                                      int64_t K, int32_t N, int64_t ld, gml_b200_stats* stats);

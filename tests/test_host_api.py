@@ -94,3 +94,18 @@ def test_no_cpu_fallback(golden):
     with pytest.raises(gml_b200.GMLB200Error) as e:
         gml_b200.learn(golden("a_samples.csv"))
     assert e.value.code == _lib.ECUDA and "no CPU fallback" in str(e.value)
+
+
+def test_matrix_entry_fails_loudly_without_device_and_validates_layout(golden):
+    """The reference-typed entry (Fortran-ordered K x (N+1) matrix) has no CPU path either; layout errors are host errors."""
+    s = np.asfortranarray(golden("a_samples.csv"))
+    with pytest.raises(ValueError):
+        gml_b200.learn_matrix(np.ascontiguousarray(golden("c_samples.csv")), gml_b200.RISE(), gml_b200.B200())   # row-major
+    with pytest.raises(ValueError):
+        gml_b200.learn_matrix(s.astype(np.float16, order="F"), gml_b200.RISE(), gml_b200.B200())
+    lib = _lib.load()
+    if lib.gml_b200_device_count() > 0:
+        pytest.skip("CUDA device present")
+    with pytest.raises(gml_b200.GMLB200Error) as e:
+        gml_b200.learn(s, gml_b200.RISE(), gml_b200.B200())        # F-ordered input takes the matrix entry
+    assert e.value.code == _lib.ECUDA
