@@ -22,7 +22,8 @@ EXPORTS = (
     "gml_b200_learn_pairwise_matrix", "gml_b200_learn_multibody_matrix", "gml_b200_upload_matrix",
     "gml_b200_create", "gml_b200_destroy", "gml_b200_upload_histogram",
     "gml_b200_attach_histogram_device", "gml_b200_num_samples", "gml_b200_solve_pairwise",
-    "gml_b200_solve_pairwise_device", "gml_b200_solve_pairwise_path", "gml_b200_solve_multibody", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
+    "gml_b200_solve_pairwise_device", "gml_b200_solve_pairwise_path", "gml_b200_solve_multibody", "gml_b200_solve_multibody_sym",
+    "gml_b200_multibody_num_sym_keys", "gml_b200_threshold_device", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
     "gml_b200_symmetrize_device",
     "gml_b200_sample_gibbs_device", "gml_b200_sample_gibbs_terms_device", "gml_b200_build_histogram_device",
     "gml_b200_comm_unique_id", "gml_b200_comm_init", "gml_b200_comm_globalize_histogram",
@@ -102,6 +103,10 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gml_b200_solve_pairwise_device.argtypes = [vp, c.c_int32, c.c_double, op, vp, vp, sp]
     lib.gml_b200_solve_pairwise_path.argtypes = [vp, c.c_int32, vp, c.c_int32, c.c_int32, op, vp, sp]
     lib.gml_b200_solve_multibody.argtypes = [vp, c.c_int32, c.c_double, op, vp, vp, sp]
+    lib.gml_b200_solve_multibody_sym.argtypes = [vp, c.c_int32, c.c_double, op, vp, vp, sp]
+    lib.gml_b200_multibody_num_sym_keys.argtypes = [c.c_int32, c.c_int32]
+    lib.gml_b200_multibody_num_sym_keys.restype = c.c_int64
+    lib.gml_b200_threshold_device.argtypes = [vp, c.c_int32, c.c_double, c.POINTER(c.c_int64), vp]
     lib.gml_b200_eval_pairwise.argtypes = [vp, c.c_int32, op, vp, vp, vp]
     lib.gml_b200_bench_passes.argtypes = [vp, c.c_int32, op, c.c_int32, vp]
     lib.gml_b200_symmetrize_device.argtypes = [vp, c.c_int32, vp]

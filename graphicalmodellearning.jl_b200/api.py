@@ -437,6 +437,33 @@ class Session:
         _lib.check(rc)
         return (vals, {"lambda": lam, "objective": obj, **method.last_stats}) if return_info else vals
 
+    def solve_multibody_sym(self, formulation, method: B200, lam: Optional[float] = None, return_info=False):
+        """multiRISE with the mean-symmetrisation of :135-149 done on the device: returns the FactorGraph over SORTED
+        keys (values zipped with the canonical enumeration: by size, then lexicographic = permutations(1:N, q))."""
+        import itertools
+        N = self.N
+        order = int(formulation.interaction_order)
+        if lam is None:
+            lam = regularizer_lambda(formulation.regularizer, N, self.num_samples)
+        n_sym = int(self._lib.gml_b200_multibody_num_sym_keys(N, order))
+        vals, obj = np.zeros(n_sym), np.zeros(N)
+        st = _lib.Stats()
+        opts = method._opts()
+        rc = self._lib.gml_b200_solve_multibody_sym(self._h, order, lam, ctypes.byref(opts), _ptr(vals), _ptr(obj), ctypes.byref(st))
+        method.last_stats = st.as_dict()
+        _lib.check(rc)
+        keys = itertools.chain.from_iterable(itertools.combinations(range(1, N + 1), q) for q in range(1, order + 1))
+        fg = FactorGraph(order, N, "spin", dict(zip(keys, vals.tolist())))
+        return (fg, {"lambda": lam, "objective": obj, **method.last_stats}) if return_info else fg
+
+    def threshold(self, theta: np.ndarray, tau: float):
+        """Post-hoc support selection on the device: zero the off-diagonal |theta| < tau; returns (theta, nnz)."""
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64)).to(f"cuda:{self.device}")
+        nnz = ctypes.c_int64(0)
+        _lib.check(self._lib.gml_b200_threshold_device(ctypes.c_void_p(t.data_ptr()), theta.shape[0], float(tau), ctypes.byref(nnz), None))
+        return t.cpu().numpy(), int(nnz.value)
+
     def eval_pairwise(self, formulation, x: np.ndarray, backend: str = "fista_tc", want_grad: bool = True,
                       coarse: bool = False):
         """f_u and grad f_u at rows x [N x (N+1)] (couplings then field).  coarse=True evaluates on the tensor-core

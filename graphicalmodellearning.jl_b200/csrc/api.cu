@@ -95,6 +95,50 @@ __global__ void multibody_gather_kernel(const double* __restrict__ x, int Fp, in
         vals[(int64_t)u * n_keys + f] = x[(int64_t)u * Fp + key_map[(int64_t)u * n_keys + f]];
 }
 
+// multiRISE symmetrisation on the device (src/GraphicalModelLearning.jl:135-149): thread i owns the i-th SORTED key S
+// (subsets of [N] of size 1..order, by size then lexicographic) and averages the |S| per-node estimates -- node u in S
+// holds its value for (u, S \ {u}) at base feature index(S \ {u}) of row u (base features are the subsets of size
+// <= order-1 in the same enumeration).  binom: (N+1) x (order+1) table; size_off[q] = first key / feature of size q.
+__device__ __forceinline__ long long comb_rank(const int* c, int r, int N, const long long* binom, int W) {
+    long long rank = 0;
+    int prev = -1;
+    for (int i = 0; i < r; ++i) {
+        for (int v = prev + 1; v < c[i]; ++v) rank += binom[(N - 1 - v) * W + (r - 1 - i)];
+        prev = c[i];
+    }
+    return rank;
+}
+__global__ void multibody_symmetrize_kernel(const double* __restrict__ x, int N, int Fp, int order, const long long* __restrict__ binom,
+                                            const long long* __restrict__ key_off /* [order+2] by key size */,
+                                            const long long* __restrict__ feat_off /* [order+1] by feature size */,
+                                            long long n_sym, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sym) return;
+    const int W = order + 1;
+    int q = 1;
+    while (q < order && i >= key_off[q + 1]) ++q;
+    long long rem = i - key_off[q];
+    int mem[8];
+    int v = 0;
+    for (int j = 0; j < q; ++j) {             // unrank the combination
+        for (;; ++v) {
+            const long long cnt = binom[(N - 1 - v) * W + (q - 1 - j)];
+            if (rem < cnt) break;
+            rem -= cnt;
+        }
+        mem[j] = v++;
+    }
+    double acc = 0.0;
+    for (int j = 0; j < q; ++j) {
+        int t[8];
+        int r = 0;
+        for (int m = 0; m < q; ++m) if (m != j) t[r++] = mem[m];
+        const long long f = feat_off[q - 1] + comb_rank(t, q - 1, N, binom, W);
+        acc += x[(long long)mem[j] * Fp + f];
+    }
+    out[i] = acc / q;
+}
+
 int64_t binom(int n, int k) {
     if (k < 0 || k > n) return 0;
     long double r = 1;
@@ -560,10 +604,10 @@ int gml_b200_solve_pairwise_path(gml_b200_handle* h, int32_t formulation, const 
     });
 }
 
-int gml_b200_solve_multibody(gml_b200_handle* h, int32_t order, double lambda, const gml_b200_opts* opts,
-                             double* out_vals, double* out_objective, gml_b200_stats* stats) {
+static int solve_multibody_impl(gml_b200_handle* h, int32_t order, double lambda, const gml_b200_opts* opts,
+                                double* out_vals, double* out_sym, double* out_objective, gml_b200_stats* stats) {
     return guarded([&] {
-        GML_REQUIRE(h && out_vals, "null argument");
+        GML_REQUIRE(h && (out_vals || out_sym), "null argument");
         GML_REQUIRE(h->has_hist, "no histogram resident: call gml_b200_upload_histogram first");
         GML_REQUIRE(order >= 1, "interaction_order must be >= 1");
         GML_REQUIRE(lambda >= 0.0 && std::isfinite(lambda), "lambda must be finite and >= 0");
@@ -593,13 +637,36 @@ int gml_b200_solve_multibody(gml_b200_handle* h, int32_t order, double lambda, c
         SolveResult r;
         int solver_used = 0;
         run_solver(p, o, r, solver_used, st);
-        DevBuf<double> vals;
-        vals.alloc((size_t)N * L.n_keys);
-        multibody_gather_kernel<<<N, 128, 0, st>>>(r.x.p, p.Fp, L.n_keys, key_map.p, vals.p);
-        GML_LAUNCHED();
+        DevBuf<double> vals, sym;
+        DevBuf<long long> tab;
+        int64_t n_sym = 0;
+        if (out_vals) {
+            vals.alloc((size_t)N * L.n_keys);
+            multibody_gather_kernel<<<N, 128, 0, st>>>(r.x.p, p.Fp, L.n_keys, key_map.p, vals.p);
+            GML_LAUNCHED();
+        }
+        if (out_sym) {
+            GML_REQUIRE(order <= 8, "device symmetrisation supports interaction_order <= 8");
+            const int W = order + 1;
+            std::vector<long long> ht((size_t)(N + 1) * W + (order + 2) + (order + 1), 0);
+            for (int n = 0; n <= N; ++n)
+                for (int k = 0; k <= order; ++k) ht[(size_t)n * W + k] = binom(n, k);
+            long long* key_off = ht.data() + (size_t)(N + 1) * W;        // by key size q = 1..order
+            long long* feat_off = key_off + (order + 2);                  // by feature size q = 0..order-1
+            for (int q = 1; q <= order; ++q) key_off[q + 1] = key_off[q] + binom(N, q);
+            for (int q = 0; q < order; ++q) feat_off[q + 1] = feat_off[q] + binom(N, q);
+            n_sym = key_off[order + 1];
+            tab.alloc(ht.size()); sym.alloc((size_t)n_sym);
+            GML_CUDA(cudaMemcpyAsync(tab.p, ht.data(), sizeof(long long) * ht.size(), cudaMemcpyHostToDevice, st));
+            multibody_symmetrize_kernel<<<(unsigned)ceil_div(n_sym, 128), 128, 0, st>>>(r.x.p, N, p.Fp, order, tab.p, tab.p + (size_t)(N + 1) * W,
+                                                                                   tab.p + (size_t)(N + 1) * W + (order + 2), n_sym, sym.p);
+            GML_LAUNCHED();
+            GML_CUDA(cudaStreamSynchronize(st));      // `ht` is read by the copy above
+        }
         const double solve_ms = timer.stop();
         EventTimer t2(st);
-        GML_CUDA(cudaMemcpyAsync(out_vals, vals.p, sizeof(double) * N * L.n_keys, cudaMemcpyDeviceToHost, st));
+        if (out_vals) GML_CUDA(cudaMemcpyAsync(out_vals, vals.p, sizeof(double) * N * L.n_keys, cudaMemcpyDeviceToHost, st));
+        if (out_sym) GML_CUDA(cudaMemcpyAsync(out_sym, sym.p, sizeof(double) * n_sym, cudaMemcpyDeviceToHost, st));
         if (out_objective) GML_CUDA(cudaMemcpyAsync(out_objective, r.objective.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
         const double d2h = t2.stop();
         finish_stats(stats, r, solver_used, N, hist.K, solve_ms, d2h, t0);
@@ -607,6 +674,50 @@ int gml_b200_solve_multibody(gml_b200_handle* h, int32_t order, double lambda, c
             set_error("solver did not reach tol within max_iter for " + std::to_string(r.n_unconverged) + " node(s)");
             throw CudaError{GML_B200_ENOTCONV};
         }
+    });
+}
+
+int gml_b200_solve_multibody(gml_b200_handle* h, int32_t order, double lambda, const gml_b200_opts* opts,
+                             double* out_vals, double* out_objective, gml_b200_stats* stats) {
+    if (!out_vals) { set_error("null argument"); return GML_B200_EINVAL; }
+    return solve_multibody_impl(h, order, lambda, opts, out_vals, nullptr, out_objective, stats);
+}
+
+int gml_b200_solve_multibody_sym(gml_b200_handle* h, int32_t order, double lambda, const gml_b200_opts* opts,
+                                 double* out_sym_vals, double* out_objective, gml_b200_stats* stats) {
+    if (!out_sym_vals) { set_error("null argument"); return GML_B200_EINVAL; }
+    return solve_multibody_impl(h, order, lambda, opts, nullptr, out_sym_vals, out_objective, stats);
+}
+
+int64_t gml_b200_multibody_num_sym_keys(int32_t N, int32_t order) {
+    int64_t n = 0;
+    for (int q = 1; q <= order; ++q) n += binom(N, q);
+    return n;
+}
+
+// |theta| < tau -> 0 off the diagonal (post-hoc support selection); counts the surviving off-diagonal entries
+__global__ void threshold_kernel(double* __restrict__ m, int N, double tau, unsigned long long* __restrict__ nnz) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * N) return;
+    const int r = (int)(i / N), c = (int)(i % N);
+    if (r == c) return;
+    if (fabs(m[i]) < tau) m[i] = 0.0;
+    else atomicAdd(nnz, 1ull);
+}
+
+int gml_b200_threshold_device(double* d_theta, int32_t N, double tau, int64_t* out_nnz, void* stream) {
+    return guarded([&] {
+        GML_REQUIRE(d_theta && N >= 1 && tau >= 0.0, "bad argument");
+        cudaStream_t st = (cudaStream_t)stream;
+        DevBuf<unsigned long long> cnt;
+        cnt.alloc(1);
+        GML_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), st));
+        threshold_kernel<<<(unsigned)ceil_div((int64_t)N * N, 256), 256, 0, st>>>(d_theta, N, tau, cnt.p);
+        GML_LAUNCHED();
+        unsigned long long hc = 0;
+        GML_CUDA(cudaMemcpyAsync(&hc, cnt.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        GML_CUDA(cudaStreamSynchronize(st));
+        if (out_nnz) *out_nnz = (int64_t)hc;
     });
 }
 

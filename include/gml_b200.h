@@ -179,6 +179,19 @@ int gml_b200_solve_multibody(gml_b200_handle* h, int32_t interaction_order, doub
                              const gml_b200_opts* opts, double* out_vals, double* out_objective,
                              gml_b200_stats* stats);
 
+/* multiRISE with the symmetrisation of src/GraphicalModelLearning.jl:135-149 done on the device: out_sym_vals[i] is the
+ * MEAN of the per-node estimates of the i-th sorted key, sorted keys enumerated by size (1..interaction_order) and then
+ * lexicographically -- the order of the reference's permutations(1:N, q) (src/models.jl:228-246), so the caller zips the
+ * values with that enumeration instead of grouping 13 080 boxed Dict entries.  n = gml_b200_multibody_num_sym_keys. */
+int gml_b200_solve_multibody_sym(gml_b200_handle* h, int32_t interaction_order, double lambda,
+                                 const gml_b200_opts* opts, double* out_sym_vals, double* out_objective,
+                                 gml_b200_stats* stats);
+int64_t gml_b200_multibody_num_sym_keys(int32_t N, int32_t interaction_order);
+
+/* Post-hoc support selection: zero the off-diagonal entries of a ROW-major N x N device matrix with
+ * |theta| < tau; *out_nnz (nullable) receives the number of surviving off-diagonal entries. */
+int gml_b200_threshold_device(double* d_theta, int32_t N, double tau, int64_t* out_nnz, void* stream);
+
 /* Objective and gradient of the smooth part f_u (src/GraphicalModelLearning.jl:170 / 279 / 317) for all nodes of
  * the shard at a caller-supplied point.  x, g_out: (node_end-node_begin) x (N+1) row-major host arrays, feature
  * order = couplings to spins 0..N-1 (the self entry is ignored / returns 0), then the local field.  `solver`
