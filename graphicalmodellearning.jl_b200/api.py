@@ -73,7 +73,8 @@ class B200(GMLMethod):
     """Batched GPU solver.  tol: stopping tolerance (prox-gradient mapping max-norm for FISTA,
     Newton step for the small-problem solver; 0 = solver default 1e-6 / 1e-12).  barrier_mu > 0
     returns the log-barrier point Ipopt stops at (use 1e-9 to reproduce the reference's stored
-    fixtures to ~1e-9) instead of the exact L1 minimiser."""
+    fixtures to ~1e-9) instead of the exact L1 minimiser; it needs the Newton solver (at most 128
+    features per node).  polish=True finishes a FISTA solve with fp64 Newton on each node's support."""
     tol: float = 0.0
     max_iter: int = 0
     solver: str = "auto"          # auto | newton | fista_cc | fista_tc
@@ -86,7 +87,8 @@ class B200(GMLMethod):
     coarse_level: bool = True     # fista_tc: 3-limb iterate / one residual limb less while far from convergence
     devices: int = 1              # one-shot learn(): shard the nodes over this many GPUs from this process
     compaction: bool = True       # FISTA: restrict the passes to the nodes that are still active (parked / converged ones drop out)
-    warm_start: bool = False      # FISTA, full pairwise solves: start from the mean-field couplings (experimental, opt-in)
+    warm_start: bool = False      # FISTA, full pairwise solves: start from the mean-field couplings (opt-in)
+    polish: bool = False          # FISTA solvers: finish every node with fp64 Newton on its identified support (exact L1 minimiser to ~1e-12)
     last_stats: dict = field(default_factory=dict, repr=False, compare=False)
 
     def _opts(self, node_begin: int = 0, node_end: int = 0, stream: int = 0) -> _lib.Opts:
@@ -105,7 +107,7 @@ class B200(GMLMethod):
         o.reserved[3] = 0 if self.coarse_level else 1
         o.reserved[4] = int(self.devices)
         o.reserved[6] = 0 if self.compaction else 1
-        o.reserved[7] = 1 if self.warm_start else 0
+        o.reserved[7] = (1 if self.warm_start else 0) | (2 if self.polish else 0)
         return o
 
 

@@ -153,18 +153,24 @@ void fill_opts(gml_b200_opts& o, const gml_b200_opts* in) {
 
 int pick_solver(const gml_b200_opts& o, int F) {
     int s = o.solver;
-    if (s == GML_B200_SOLVER_AUTO) s = (F <= NEWTON_MAX_F) ? GML_B200_SOLVER_NEWTON : GML_B200_SOLVER_FISTA_TC;
+    // AUTO: the fp64 Newton solver for small problems; the Ipopt-compatible barrier point needs it (up to 128 features)
+    if (s == GML_B200_SOLVER_AUTO)
+        s = (F <= NEWTON_AUTO_F || (o.barrier_mu > 0.0 && F <= NEWTON_MAX_F)) ? GML_B200_SOLVER_NEWTON : GML_B200_SOLVER_FISTA_TC;
     GML_REQUIRE(s >= GML_B200_SOLVER_NEWTON && s <= GML_B200_SOLVER_FISTA_TC, "unknown solver id");
-    GML_REQUIRE(s != GML_B200_SOLVER_NEWTON || F <= NEWTON_MAX_F, "Newton solver needs <= 64 features per node");
+    GML_REQUIRE(s != GML_B200_SOLVER_NEWTON || F <= NEWTON_MAX_F, "Newton solver needs <= 128 features per node");
     GML_REQUIRE(o.barrier_mu == 0.0 || s == GML_B200_SOLVER_NEWTON,
-                "barrier_mu (Ipopt-compatible mode) is only available with the Newton solver (<= 64 features)");
+                "barrier_mu (Ipopt-compatible mode) is only available with the Newton solver (<= 128 features per node); "
+                "beyond that use the exact minimiser, optionally with the support polish (opts.reserved[7] & 2)");
     return s;
 }
 
 void run_solver(const NodeProblem& p, const gml_b200_opts& o, SolveResult& r, int& solver_used, cudaStream_t st) {
     solver_used = pick_solver(o, p.F);
-    if (solver_used == GML_B200_SOLVER_NEWTON) solve_newton(p, o, r, st);
-    else solve_fista(p, o, solver_used, r, st);
+    if (solver_used == GML_B200_SOLVER_NEWTON) { solve_newton(p, o, r, st); return; }
+    const bool polish = (o.reserved[7] & 2) != 0;       // FISTA to tol, then reduced-space Newton on the support
+    r.want_grad_at_x = polish;
+    solve_fista(p, o, solver_used, r, st);
+    if (polish && r.n_unconverged == 0) polish_on_support(p, o, r, st);
 }
 
 }  // namespace
@@ -232,7 +238,7 @@ void solve_pairwise_rows_one(gml_b200_handle* h, int formulation, double lambda,
     if (o.reserved[2] == 1) {
         GML_REQUIRE(h->comm != nullptr, "sample-sharded solve needs gml_b200_comm_init first");
         GML_REQUIRE(hist.M_local > 0.0, "sample-sharded solve needs gml_b200_comm_globalize_histogram after the upload");
-        GML_REQUIRE(o.solver == GML_B200_SOLVER_FISTA_TC || (o.solver == GML_B200_SOLVER_AUTO && p.F > NEWTON_MAX_F),
+        GML_REQUIRE(o.solver == GML_B200_SOLVER_FISTA_TC || (o.solver == GML_B200_SOLVER_AUTO && p.F > NEWTON_AUTO_F),
                     "sample-sharded mode is implemented for the tensor-core FISTA solver");
         p.comm = h->comm;
     }
@@ -270,7 +276,7 @@ void solve_pairwise_rows(gml_b200_handle* h, int formulation, double lambda, con
     const int N = hist.N;
     GML_REQUIRE(nb >= 0 && ne <= N && nb < ne, "node shard out of range");
     const int F = N + 1;
-    int solver = o.solver == GML_B200_SOLVER_AUTO ? (F <= NEWTON_MAX_F ? GML_B200_SOLVER_NEWTON : GML_B200_SOLVER_FISTA_TC) : o.solver;
+    int solver = pick_solver(o, F);
     int chunk = ne - nb;
     if (solver == GML_B200_SOLVER_FISTA_TC && !warm && o.reserved[2] != 1) {
         size_t free_b = 0, total_b = 0;
@@ -994,7 +1000,7 @@ int gml_b200_learn_pairwise(const double* counts, const int8_t* spins, int64_t K
         // Partition: sample slices when every device still gets a GPU-filling number of rows -- each device
         // then streams K/n rows per pass instead of all K -- else node shards with the histogram replicated.
         // opts->reserved[2] = 2 forces node shards.
-        const bool tc = (opts->solver == GML_B200_SOLVER_AUTO && N + 1 > NEWTON_MAX_F) || opts->solver == GML_B200_SOLVER_FISTA_TC;
+        const bool tc = (opts->solver == GML_B200_SOLVER_AUTO && N + 1 > NEWTON_AUTO_F) || opts->solver == GML_B200_SOLVER_FISTA_TC;
         if (n_dev > 1 && tc && opts->reserved[2] != 2 && K / n_dev >= 65536 && opts->barrier_mu == 0.0) {
             HostSource src;
             src.counts = counts; src.spins = spins; src.ld = ld;
@@ -1049,7 +1055,7 @@ int gml_b200_learn_pairwise_matrix(const void* samples, int32_t dtype, int64_t K
     src.matrix = samples; src.dtype = dtype; src.ld = ld; src.regularizer = regularizer;
     if (opts && opts->reserved[4] > 1) {
         const int n_dev = std::min<int>(opts->reserved[4], std::max(1, gml_b200_device_count() - opts->device));
-        const bool tc = (opts->solver == GML_B200_SOLVER_AUTO && N + 1 > NEWTON_MAX_F) || opts->solver == GML_B200_SOLVER_FISTA_TC;
+        const bool tc = (opts->solver == GML_B200_SOLVER_AUTO && N + 1 > NEWTON_AUTO_F) || opts->solver == GML_B200_SOLVER_FISTA_TC;
         if (n_dev > 1 && tc && K / n_dev >= 65536 && opts->barrier_mu == 0.0) {
             const int rc = learn_pairwise_multi_device_samples(src, K, N, formulation, 0.0, symmetrize, *opts, n_dev, out_theta,
                                                                out_objective, stats);

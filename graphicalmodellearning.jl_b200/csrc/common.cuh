@@ -113,7 +113,10 @@ struct NodeProblem {
     int32_t Nn = 0;                 // nodes in this shard
     DevBuf<int32_t> spin_row;       // [Nn] row of hist->base that holds s_u
     DevBuf<uint8_t> pen;            // [Nn x Fp] penalty class per coordinate (padded features = PEN_ZERO)
-    const double* x0 = nullptr;     // optional warm start [Nn x Fp] (FISTA solvers; e.g. the previous point of a lambda path)
+    const double* x0 = nullptr;     // optional warm start [Nn x Fp] (e.g. the previous point of a lambda path)
+    // Reduced-space problems (support polish): node u's feature f is row feat[u * Fp + f] of Q instead of row f
+    // (Newton solver only; nullptr = the shared feature order).
+    const int32_t* feat = nullptr;
 };
 
 struct SolveResult {
@@ -124,6 +127,9 @@ struct SolveResult {
     int iterations = 0, n_fg = 0, n_f = 0, n_unconverged = 0;
     int n_stalled = 0;        // nodes accepted at the gradient noise floor with tol < residual <= 10 tol
     int n_out_of_range = 0;   // nodes re-solved by the CUDA-core backend because they left the fixed-point range
+    int n_unpolished = 0;     // support polish: nodes whose support exceeded the reduced solver's 64 features (FISTA point kept)
+    DevBuf<double> grad;      // [Nn x Fp] gradient of the smooth part at x (filled by solve_fista when want_grad_at_x)
+    bool want_grad_at_x = false;
     double max_residual = 0.0;
 };
 
@@ -147,8 +153,12 @@ void ingest_matrix(const void* samples, int dtype, int64_t ld, int64_t k0, int64
                    double* d_counts, int n_threads, double* out_host_ms);
 
 // --- newton.cu : fp64 proximal-Newton / barrier-Newton for small feature counts
-constexpr int NEWTON_MAX_F = 64;
+constexpr int NEWTON_MAX_F = 128;    // feature limit of the fp64 Newton solver (dense F x F Hessian per node in shared memory)
+constexpr int NEWTON_AUTO_F = 64;    // solver = AUTO takes the Newton solver up to this many features, FISTA beyond
 void solve_newton(const NodeProblem& p, const gml_b200_opts& o, SolveResult& r, cudaStream_t st);
+
+// --- polish.cu : reduced-space Newton polish of a FISTA solution on its identified support (exact or barrier point)
+void polish_on_support(const NodeProblem& p, const gml_b200_opts& o, SolveResult& r, cudaStream_t st);
 
 // --- fista.cu : batched FISTA driver over an evaluation backend
 void solve_fista(const NodeProblem& p, const gml_b200_opts& o, int backend, SolveResult& r, cudaStream_t st);

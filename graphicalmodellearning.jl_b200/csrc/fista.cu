@@ -370,7 +370,7 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
         be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += pass_units();
         // Opt-in (opts.reserved[7]): cold full pairwise solve -> start from the mean-field couplings read off the
         // gradient at 0 (= minus the pair correlations), see warmstart.cu.  One more pass, ~30 % fewer rounds expected.
-        if (li == 0 && strides.size() == 1 && !prob.x0 && o.reserved[7] != 0 && Nn == hist.N && prob.Q == hist.base.p &&
+        if (li == 0 && strides.size() == 1 && !prob.x0 && (o.reserved[7] & 1) != 0 && Nn == hist.N && prob.Q == hist.base.p &&
             prob.F == hist.N + 1) {
             const double xmax = level == 0 ? 0.9 : 7.0;
             if (meanfield_start(G.p, Nn, Fp, prob.pen.p, xmax, s.lattice, Y.p, st)) {
@@ -455,8 +455,15 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
     if (o.verbose > 0) { GML_CUDA(cudaStreamSynchronize(st)); t_loop = tick(); }
     // objective at the returned point (all nodes)
     be->set_active(nullptr, 0, st);
-    be->eval(r.x.p, false, fYn.p, nullptr, st); ++n_f;
-    r.fg_units = fg_units; r.f_units = 1.0;
+    if (r.want_grad_at_x) {          // the support polish reads the gradient at the returned point
+        r.grad.alloc(nx);
+        be->eval(r.x.p, true, fYn.p, r.grad.p, st); ++n_fg; fg_units += 1.0;
+        r.f_units = 0.0;
+    } else {
+        be->eval(r.x.p, false, fYn.p, nullptr, st); ++n_f;
+        r.f_units = 1.0;
+    }
+    r.fg_units = fg_units;
     fista_objective_kernel<<<Nn, 128, 0, st>>>(s, fYn.p);
     GML_LAUNCHED();
 

@@ -1,5 +1,5 @@
 // K5: small-problem solver.  fp64 proximal Newton (exact L1 minimiser) and damped barrier Newton
-// (the log-barrier point Ipopt returns) for node problems with at most NEWTON_MAX_F features.
+// (the log-barrier point Ipopt returns) for node problems with at most NEWTON_MAX_F (128) features.
 //
 // This is the device counterpart of what the reference asks Ipopt to do per node
 // (src/GraphicalModelLearning.jl:164-181): every outer iteration evaluates f, grad f and the dense
@@ -21,6 +21,7 @@ struct NewtonParams {
     const double* w;           // [Kp]
     const int32_t* spin_row;   // [Nn]
     const uint8_t* pen;        // [Nn x Fp]
+    const int32_t* feat;       // [Nn x Fp] per-node feature rows (reduced-space problems) or nullptr
     int64_t Kp;
     int F, Fp, Nn, chunks;
     int64_t chunk_len;         // multiple of TS
@@ -71,7 +72,11 @@ __global__ void __launch_bounds__(NT) newton_accum_kernel(NewtonParams p, int fo
     __shared__ double s_x[NEWTON_MAX_F];
     __shared__ double s_red[NT / 32];
     const int tid = threadIdx.x;
-    if (tid < F) s_x[tid] = p.x[(int64_t)u * p.Fp + tid];
+    __shared__ int s_feat[NEWTON_MAX_F];
+    if (tid < F) {
+        s_x[tid] = p.x[(int64_t)u * p.Fp + tid];
+        s_feat[tid] = p.feat ? p.feat[(int64_t)u * p.Fp + tid] : tid;
+    }
 
     // owned entries: e in [0,F) gradient, e >= F Hessian pair (a >= b)
     int ea[NE], eb[NE];
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(NT) newton_accum_kernel(NewtonParams p, int fo
             const int su = srow[k];
             double m = 0.0;
             for (int f = 0; f < F; ++f) {
-                const int q = p.Q[(int64_t)f * p.Kp + k];
+                const int q = p.Q[(int64_t)s_feat[f] * p.Kp + k];
                 stat[tid][f] = (int8_t)(su * q);
                 m += s_x[f] * (double)q;
             }
@@ -319,7 +324,11 @@ __global__ void __launch_bounds__(NT) newton_linesearch_kernel(NewtonParams p, i
     const int F = p.F, tid = threadIdx.x;
     __shared__ double s_x[NEWTON_MAX_F], s_d[NEWTON_MAX_F];
     __shared__ double s_red[NT / 32][NALPHA];
-    if (tid < F) { s_x[tid] = p.x[(int64_t)u * p.Fp + tid]; s_d[tid] = p.d[(int64_t)u * p.Fp + tid]; }
+    __shared__ int s_feat[NEWTON_MAX_F];
+    if (tid < F) {
+        s_x[tid] = p.x[(int64_t)u * p.Fp + tid]; s_d[tid] = p.d[(int64_t)u * p.Fp + tid];
+        s_feat[tid] = p.feat ? p.feat[(int64_t)u * p.Fp + tid] : tid;
+    }
     __syncthreads();
     double acc[NALPHA];
 #pragma unroll
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(NT) newton_linesearch_kernel(NewtonParams p, i
         const double su = srow[k];
         double mx = 0.0, md = 0.0;
         for (int f = 0; f < F; ++f) {
-            const double q = p.Q[(int64_t)f * p.Kp + k];
+            const double q = p.Q[(int64_t)s_feat[f] * p.Kp + k];
             mx += s_x[f] * q; md += s_d[f] * q;
         }
         const double w = p.w[k];
@@ -424,7 +433,9 @@ void launch_accum(const NewtonParams& P, int form, cudaStream_t st) {
     else if (ne <= 2) newton_accum_kernel<2><<<grid, NT, 0, st>>>(P, form);
     else if (ne <= 3) newton_accum_kernel<3><<<grid, NT, 0, st>>>(P, form);
     else if (ne <= 5) newton_accum_kernel<5><<<grid, NT, 0, st>>>(P, form);
-    else newton_accum_kernel<9><<<grid, NT, 0, st>>>(P, form);
+    else if (ne <= 9) newton_accum_kernel<9><<<grid, NT, 0, st>>>(P, form);
+    else if (ne <= 17) newton_accum_kernel<17><<<grid, NT, 0, st>>>(P, form);
+    else newton_accum_kernel<33><<<grid, NT, 0, st>>>(P, form);      // F <= 128: F + F(F+1)/2 <= 33 * 256
     GML_LAUNCHED();
 }
 
@@ -433,7 +444,7 @@ void launch_accum(const NewtonParams& P, int form, cudaStream_t st) {
 void solve_newton(const NodeProblem& prob, const gml_b200_opts& o, SolveResult& r, cudaStream_t st) {
     const Histogram& h = *prob.hist;
     const int F = prob.F, Fp = prob.Fp, Nn = prob.Nn;
-    GML_REQUIRE(F <= NEWTON_MAX_F, "Newton solver supports at most 64 features per node");
+    GML_REQUIRE(F <= NEWTON_MAX_F, "Newton solver supports at most 128 features per node");
     const int Ptot = 1 + F + F * (F + 1) / 2;
     int64_t chunks = ceil_div(h.Kp, 1024);
     chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, 1184 / Nn));
@@ -450,13 +461,14 @@ void solve_newton(const NodeProblem& prob, const gml_b200_opts& o, SolveResult& 
     part_ls.alloc((size_t)Nn * chunks * NALPHA);
     fcur.alloc(Nn); slope.alloc(Nn); resid.alloc(Nn);
     conv.alloc(Nn); n_active.alloc(1);
-    GML_CUDA(cudaMemsetAsync(r.x.p, 0, sizeof(double) * Nn * Fp, st));
+    if (prob.x0) GML_CUDA(cudaMemcpyAsync(r.x.p, prob.x0, sizeof(double) * Nn * Fp, cudaMemcpyDeviceToDevice, st));
+    else GML_CUDA(cudaMemsetAsync(r.x.p, 0, sizeof(double) * Nn * Fp, st));
     GML_CUDA(cudaMemsetAsync(d.p, 0, sizeof(double) * Nn * Fp, st));
     GML_CUDA(cudaMemsetAsync(conv.p, 0, sizeof(int) * Nn, st));
     GML_CUDA(cudaMemsetAsync(resid.p, 0, sizeof(double) * Nn, st));
 
     NewtonParams P{};
-    P.Q = prob.Q; P.base = h.base.p; P.w = h.w64.p; P.spin_row = prob.spin_row.p; P.pen = prob.pen.p;
+    P.Q = prob.Q; P.base = h.base.p; P.w = h.w64.p; P.spin_row = prob.spin_row.p; P.pen = prob.pen.p; P.feat = prob.feat;
     P.Kp = h.Kp; P.F = F; P.Fp = Fp; P.Nn = Nn; P.chunks = (int)chunks; P.chunk_len = chunk_len;
     P.lambda = prob.lambda; P.mu = o.barrier_mu;
     P.x = r.x.p; P.d = d.p; P.part = part.p; P.part_ls = part_ls.p; P.fcur = fcur.p; P.slope = slope.p;

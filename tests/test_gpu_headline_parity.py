@@ -300,3 +300,51 @@ def test_device_multirise_symmetrisation_and_threshold(golden):
     cut, nnz = sess.threshold(theta, 0.15)
     expect = np.where((np.abs(theta) < 0.15) & ~np.eye(4, dtype=bool), 0.0, theta)
     assert np.array_equal(cut, expect) and nnz == int(np.count_nonzero(expect - np.diag(np.diag(expect))))
+
+
+# ------------------------------------------------------------------------------------------------
+# (f) second-order finishes beyond 64 features: barrier point up to 128 features, support polish for any size
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def n100():
+    from test_gpu_fullsize import lattice_model
+    truth, _, _, _ = lattice_model()
+    spins = gibbs_pairwise(truth, 20_000, 60, 100).cpu().numpy()
+    return np.ones(spins.shape[1]), spins
+
+
+def test_barrier_point_n100_passes_the_reference_isapprox(n100):
+    """B200(barrier_mu=1e-9) at N = 100 (101 features per node: the fp64 Newton solver with the dense 101 x 101 Hessian)
+    against the oracle's barrier point -- the criterion of the reference's own known-answer tests
+    (test/runtests.jl:77,89,95,101: isapprox, relative Frobenius <= sqrt(eps))."""
+    counts, spins = n100
+    lam = gml_b200.regularizer_lambda(0.4, 100, counts.sum())
+    got, info = gml_b200.learn_packed(counts, spins, RISE(0.4, False), B200(barrier_mu=1e-9), lam=lam, return_info=True)
+    assert info["solver_used"] == 1
+    ref = c.learn_pairwise_packed(counts, spins, "RISE", lam, False, mode="barrier", mu=1e-9)
+    assert np.linalg.norm(got - ref) <= np.sqrt(np.finfo(float).eps) * np.linalg.norm(ref)
+    assert np.abs(got - ref).max() <= 1e-8
+    for form, creg in (("logRISE", 0.8), ("RPLE", 0.2)):
+        lam = gml_b200.regularizer_lambda(creg, 100, counts.sum())
+        got = gml_b200.learn_packed(counts, spins, FORMS[form](creg, False), B200(barrier_mu=1e-9), lam=lam)
+        ref = c.learn_pairwise_packed(counts, spins, form, lam, False, mode="barrier", mu=1e-9, nodes=(40, 48))
+        assert np.linalg.norm(got[40:48] - ref[40:48]) <= np.sqrt(np.finfo(float).eps) * np.linalg.norm(ref[40:48])
+    with pytest.raises(gml_b200.GMLB200Error):                     # beyond 128 features the barrier point is refused, loudly
+        gml_b200.learn_packed(np.ones(500), np.ones((130, 500), dtype=np.int8), RISE(), B200(barrier_mu=1e-9))
+
+
+@pytest.mark.parametrize("form,creg", [("RISE", 0.4), ("logRISE", 0.8), ("RPLE", 0.2)])
+def test_support_polish_reaches_the_exact_minimiser(n200, form, creg):
+    """FISTA to 1e-5, then fp64 Newton on each node's identified support (csrc/polish.cu): the oracle's exact L1 minimiser
+    to 1e-9 at N = 200 (201 features per node, supports of a few dozen)."""
+    _, counts, spins, sess = n200
+    m = B200(solver="fista_tc", tol=1e-5, polish=True)
+    got, info = sess.solve_pairwise(FORMS[form](creg, False), m, return_info=True)
+    assert info["n_unconverged"] == 0
+    worst, worst_obj = 0.0, 0.0
+    for b, e in ((0, 2), (64, 65), (198, 200)):
+        ref, rinfo = c.learn_pairwise_packed(counts, spins, form, info["lambda"], False, nodes=(b, e), return_info=True)
+        worst = max(worst, np.abs(got[b:e] - ref[b:e]).max())
+        worst_obj = max(worst_obj, rel(info["objective"][b:e], rinfo["objective"][b:e], form))
+    print(f"polish N=200 {form}: max |dtheta| {worst:.2e}, objective rel {worst_obj:.2e}")
+    assert worst <= 1e-9 and worst_obj <= 1e-11
