@@ -476,7 +476,7 @@ class Session:
         f = np.zeros(self.N)
         g = np.zeros_like(x) if want_grad else None
         opts = B200(solver=backend)._opts()
-        opts.reserved[5] = 1 if coarse else 0
+        opts.reserved[5] = {False: 0, True: 1, "rough": 2}[coarse]
         _lib.check(self._lib.gml_b200_eval_pairwise(self._h, form_id, ctypes.byref(opts), _ptr(x), _ptr(f),
                                                     _ptr(g) if want_grad else None))
         return f, g
@@ -487,7 +487,7 @@ class Session:
         form_id = {RISE: 0, logRISE: 1, RPLE: 2}[type(formulation)]
         out = np.zeros(4)
         opts = B200(solver=backend)._opts(node_begin, node_end)
-        opts.reserved[5] = 1 if coarse else 0
+        opts.reserved[5] = {False: 0, True: 1, "rough": 2}[coarse]
         _lib.check(self._lib.gml_b200_bench_passes(self._h, form_id, ctypes.byref(opts), reps, _ptr(out)))
         return dict(zip(("energy_full", "grad", "energy_obj", "full_pass_wall"), out.tolist()))
 

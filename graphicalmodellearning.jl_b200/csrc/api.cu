@@ -752,6 +752,8 @@ int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b2
         std::unique_ptr<EvalBackend> be(o.solver == GML_B200_SOLVER_FISTA_TC ? make_backend_tc(p, st) : make_backend_cc(p, st));
         if (o.reserved[5] == 1)      // evaluate on the coarse precision level (lattice 2^-20, |x| < 1)
             GML_REQUIRE(be->set_level(0, st), "this backend has no coarse precision level");
+        if (o.reserved[5] == 2)      // ... on the rough level (lattice 2^-13, |x| < 1, one residual digit plane)
+            GML_REQUIRE(be->set_level(-1, st), "the rough precision level is not available for this backend / histogram (it needs near-uniform counts)");
         std::vector<double> hx((size_t)p.Nn * p.Fp, 0.0);
         const double lat = be->lattice(), xmax = be->x_range();
         for (int u = 0; u < p.Nn; ++u)
@@ -805,6 +807,7 @@ int gml_b200_bench_passes(gml_b200_handle* h, int32_t formulation, const gml_b20
         dx.alloc(nx); df.alloc(p.Nn); dg.alloc(nx);
         GML_CUDA(cudaMemsetAsync(dx.p, 0, sizeof(double) * nx, st));
         if (o.reserved[5] == 1) be->set_level(0, st);   // time the coarse precision level
+        if (o.reserved[5] == 2) be->set_level(-1, st);  // ... the rough one
         be->eval(dx.p, true, df.p, dg.p, st);    // warm-up
         be->eval(dx.p, false, df.p, nullptr, st);
         be->set_profiling(true);

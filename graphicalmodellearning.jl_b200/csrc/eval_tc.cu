@@ -207,7 +207,9 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_unsign
 // Two precision levels of the iterate:
 //   fine   : lattice 2^-24, |x| < 8, 4 limbs (28 bits)      -- final rounds
 //   coarse : lattice 2^-20, |x| < 1, 3 limbs (21 bits)      -- while the gradient mapping is >> the lattice
-constexpr double X_LATTICE_FINE = 1.0 / 16777216.0, X_LATTICE_COARSE = 1.0 / 1048576.0;
+//   rough  : lattice 2^-13, |x| < 1, 2 limbs (14 bits), ONE residual digit plane (8 bits) -- the first rounds of a cold
+//            start, where the iterate moves by >> 1e-4 per round and a gradient noise of ~1e-5 is irrelevant
+constexpr double X_LATTICE_FINE = 1.0 / 16777216.0, X_LATTICE_COARSE = 1.0 / 1048576.0, X_LATTICE_ROUGH = 1.0 / 8192.0;
 constexpr int X_LIMBS_MAX = 4;
 // representable range of the balanced base-128 limbs: 3 limbs hold |q| <= 1040000 (x 2^-20), 4 limbs |q| <= 134000000 (x 2^-24)
 constexpr double X_RANGE_COARSE = 0.99, X_RANGE_FINE = 7.9;
@@ -216,11 +218,11 @@ constexpr int NODE_TILE2 = 128;                  // nodes per gradient tile (M =
 
 // residual grid: |q| <= r_qmax(nR), stored as q + r_bias(nR) in nR unsigned bytes (nR <= 3 round with the
 // magic-number trick, which needs |q| < 2^22)
-__host__ __device__ constexpr int r_qmax(int nR) { return nR == 2 ? 32000 : (nR == 3 ? 4000000 : 1000000000); }
+__host__ __device__ constexpr int r_qmax(int nR) { return nR == 1 ? 120 : (nR == 2 ? 32000 : (nR == 3 ? 4000000 : 1000000000)); }
 // The biases of nR <= 3 are the ones the rounding constant provides for free: float_as_int(q + 1.5 * 2^23 [+ 2^15])
 // holds q + 2^22 [+ 2^15] in its mantissa bits, so the stored bytes are plain byte extracts of that word.
-__host__ __device__ constexpr unsigned r_bias(int nR) { return nR == 2 ? 0x8000u : (nR == 3 ? 0x400000u : 0x80000000u); }
-__host__ __device__ constexpr float r_magic(int nR) { return nR == 2 ? 12582912.f + 32768.f : 12582912.f; }
+__host__ __device__ constexpr unsigned r_bias(int nR) { return nR == 1 ? 0x80u : (nR == 2 ? 0x8000u : (nR == 3 ? 0x400000u : 0x80000000u)); }
+__host__ __device__ constexpr float r_magic(int nR) { return nR == 1 ? 12582912.f + 128.f : (nR == 2 ? 12582912.f + 32768.f : 12582912.f); }
 
 __device__ __forceinline__ int balanced_digit(int& q) {   // returns q mod 128 in [-64, 63], q <- (q - d) / 128
     const int d = ((q + 64) & 127) - 64;
@@ -240,13 +242,13 @@ __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __rest
     const bool live = slot < Nn && u >= 0;
     __shared__ double red[4];
     // largest |q| that xl balanced base-128 digits can hold
-    const long long qcap = xl == 3 ? 1040000LL : 134000000LL;
+    const long long qcap = xl == 2 ? 8100LL : (xl == 3 ? 1040000LL : 134000000LL);
     double l1 = 0.0;
     for (int f = threadIdx.x; f < Fp; f += blockDim.x) {
         const double v = live ? x[(int64_t)u * Fp + f] : 0.0;
         l1 += fabs(v);
         long long ql = llrint(v * inv_lattice);
-        if (ql > qcap || ql < -qcap) { atomicOr(flags, xl == 3 ? 2 : 1); ql = ql > 0 ? qcap : -qcap; }
+        if (ql > qcap || ql < -qcap) { atomicOr(flags, xl <= 3 ? 2 : 1); ql = ql > 0 ? qcap : -qcap; }
         int q = (int)ql;
         int d[X_LIMBS_MAX];
         for (int j = xl - 1; j > 0; --j) d[j] = balanced_digit(q);
@@ -372,11 +374,11 @@ __device__ __forceinline__ void energy_epilogue_math(const EnergyParams& p, uint
         int32_t a0[16], a1[16], a2[16], a3[16];
         tmem_ld16(tbase + 0 * NODE_TILE1 + c * 16, a0);
         tmem_ld16(tbase + 1 * NODE_TILE1 + c * 16, a1);
-        tmem_ld16(tbase + 2 * NODE_TILE1 + c * 16, a2);
+        if (XL >= 3) tmem_ld16(tbase + 2 * NODE_TILE1 + c * 16, a2);
         if (XL == 4) tmem_ld16(tbase + 3 * NODE_TILE1 + c * 16, a3);
         tmem_ld_wait();
         if (c == NPT / 16 - 1) release();         // accumulator fully read: hand it back to the MMA warp
-        if (GML_DBG(p, 32)) { facc[0] += __int_as_float(a0[0] ^ a1[3] ^ a2[7] ^ (XL == 4 ? a3[11] : 0)); continue; }   // ablation: TMEM reads only
+        if (GML_DBG(p, 32)) { facc[0] += __int_as_float(a0[0] ^ a1[3] ^ (XL >= 3 ? a2[7] : 0) ^ (XL == 4 ? a3[11] : 0)); continue; }   // ablation: TMEM reads only
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int nit = c * 16 + i;                           // node within this thread's slice
@@ -384,7 +386,8 @@ __device__ __forceinline__ void energy_epilogue_math(const EnergyParams& p, uint
             const uint32_t sgn = ((i & 3) == 3 ? sw[i >> 2] : (sw[i >> 2] << (24 - 8 * (i & 3)))) & 0x80000000u;
             // recombine the limb sums: exact integers, at most one rounding
             float e;
-            if (XL == 3) e = __int2float_rn((a0[i] * 128 + a1[i]) * 128 + a2[i]);
+            if (XL == 2) e = __int2float_rn(a0[i] * 128 + a1[i]);
+            else if (XL == 3) e = __int2float_rn((a0[i] * 128 + a1[i]) * 128 + a2[i]);
             else e = fmaf(__int2float_rn(a0[i] * 128 + a1[i]), 16384.f, __int2float_rn(a2[i] * 128 + a3[i]));
             const float es = __uint_as_float(__float_as_uint(e) ^ sgn);        // s_u * E / lattice
             float fterm, gterm;
@@ -602,13 +605,14 @@ __device__ __forceinline__ void energy_chunk_math(const EnergyParams& p, int32_t
                                                   int node0, float wk, float* __restrict__ facc) {
     const float c_arg = -p.lattice * 1.4426950408889634f;
     constexpr unsigned R_BIAS = r_bias(NR);
-    if (GML_DBG(p, 32)) { facc[0] += __int_as_float(a[0][0] ^ a[1][3] ^ a[2][7] ^ (XL == 4 ? a[3][5] : 0)); return; }
+    if (GML_DBG(p, 32)) { facc[0] += __int_as_float(a[0][0] ^ a[1][3] ^ (XL >= 3 ? a[2][7] : 0) ^ (XL == 4 ? a[3][5] : 0)); return; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const uint32_t w = i < 4 ? sw0 : sw1;
         const uint32_t sb_top = (i & 3) == 3 ? w : (w << (24 - 8 * (i & 3)));      // spin byte (0x01 / 0xFF / 0x00) in the top byte
         float e;
-        if (XL == 3) e = __int2float_rn((a[0][i] * 128 + a[1][i]) * 128 + a[2][i]);
+        if (XL == 2) e = __int2float_rn(a[0][i] * 128 + a[1][i]);
+        else if (XL == 3) e = __int2float_rn((a[0][i] * 128 + a[1][i]) * 128 + a[2][i]);
         else e = fmaf(__int2float_rn(a[0][i] * 128 + a[1][i]), 16384.f, __int2float_rn(a[2][i] * 128 + a[3][i]));
         const float es = flip_sign(e, sb_top);
         float fterm, gterm;
@@ -1214,7 +1218,7 @@ struct BackendTC : EvalBackend {
     int Nn_pad1, Nn_pad2, nR, n_sms;   // nR: residual limbs of the fine level
     int level = 1;                      // 0 = coarse (3-limb iterate, nR-1 residual limbs), 1 = fine
     int32_t first_row = 0;   // spin rows of this shard are contiguous in `base`: spin_row[u] = first_row + u
-    DevBuf<int8_t> X4, X3, R;
+    DevBuf<int8_t> X4, X3, X2, R;
     DevBuf<float> inv_dr;
     DevBuf<double> delta;
     DevBuf<double> fsum;
@@ -1233,7 +1237,7 @@ struct BackendTC : EvalBackend {
     const int8_t* spin_blocked = nullptr;
     int Fspin = 0;
     DevBuf<int8_t> base_blocked;
-    CUtensorMap tmA, tmB, tmB3, tmBh, tmB3h, tmS, tmSv, tmRa, tmQ, tmQ256;
+    CUtensorMap tmA, tmB, tmB3, tmB2, tmBh, tmB3h, tmB2h, tmS, tmSv, tmRa, tmQ, tmQ256;
     bool pair_ok = false;               // the CTA-pair energy kernel applies (limb half-tile fits: Fp <= E2_MAX_FP)
     bool spin_vec = false;
 
@@ -1250,6 +1254,7 @@ struct BackendTC : EvalBackend {
         P = ensure_P(h, p.Q, p.Fp, st);
         X4.alloc((size_t)Nn_pad1 * 4 * p.Fp);
         X3.alloc((size_t)Nn_pad1 * 3 * p.Fp);
+        X2.alloc((size_t)Nn_pad1 * 2 * p.Fp);
         R.alloc((size_t)nR * Nn_pad2 * h.Kp);
         inv_dr.alloc(Nn_pad1); delta.alloc(Nn_pad1);
         fsum.alloc(Nn_pad1);
@@ -1265,6 +1270,8 @@ struct BackendTC : EvalBackend {
         tmB3 = make_map_2d(X3.p, p.Fp, (uint64_t)Nn_pad1 * 3, 128, 3 * NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_128B);
         tmBh = make_map_2d(X4.p, p.Fp, (uint64_t)Nn_pad1 * 4, 128, 4 * 32, CU_TENSOR_MAP_SWIZZLE_128B);
         tmB3h = make_map_2d(X3.p, p.Fp, (uint64_t)Nn_pad1 * 3, 128, 3 * 32, CU_TENSOR_MAP_SWIZZLE_128B);
+        tmB2 = make_map_2d(X2.p, p.Fp, (uint64_t)Nn_pad1 * 2, 128, 2 * NODE_TILE1, CU_TENSOR_MAP_SWIZZLE_128B);
+        tmB2h = make_map_2d(X2.p, p.Fp, (uint64_t)Nn_pad1 * 2, 128, 2 * 32, CU_TENSOR_MAP_SWIZZLE_128B);
         pair_ok = p.Fp <= E2_MAX_FP && !std::getenv("GML_B200_NO_PAIR");
         // Sample-blocked layouts: every TMA box is one contiguous 8/16 KB chunk (one 2 MB page) instead of
         // 64/128 rows that are Kp bytes apart.
@@ -1310,6 +1317,13 @@ struct BackendTC : EvalBackend {
         GML_TC_SET(GML_B200_RISE, 3); GML_TC_SET(GML_B200_RISE, 4);
         GML_TC_SET(GML_B200_RPLE, 3); GML_TC_SET(GML_B200_RPLE, 4);
 #undef GML_TC_SET
+        // rough level: 2 iterate limbs, 1 residual digit plane
+        set_smem(tc_energy_kernel<GML_B200_RISE, false, 2, 1>, E_SMEM); set_smem(tc_energy_kernel<GML_B200_RISE, true, 2, 1>, E_SMEM);
+        set_smem(tc_energy_kernel<GML_B200_RPLE, false, 2, 1>, E_SMEM); set_smem(tc_energy_kernel<GML_B200_RPLE, true, 2, 1>, E_SMEM);
+        set_smem(tc_energy_pair_kernel<GML_B200_RISE, false, 2, 1>, e2_smem(2)); set_smem(tc_energy_pair_kernel<GML_B200_RISE, true, 2, 1>, e2_smem(2));
+        set_smem(tc_energy_pair_kernel<GML_B200_RPLE, false, 2, 1>, e2_smem(2)); set_smem(tc_energy_pair_kernel<GML_B200_RPLE, true, 2, 1>, e2_smem(2));
+        set_smem(tc_grad_kernel<1, 256>, grad_smem(1, 256));
+        set_smem(tc_grad_kernel<1, 128>, grad_smem(1, 128));
         set_smem(tc_grad_kernel<2, 128>, grad_smem(2, 128));
         set_smem(tc_grad_kernel<2, 256>, grad_smem(2, 256));
         set_smem(tc_grad_kernel<3, 128>, grad_smem(3, 128));
@@ -1330,18 +1344,22 @@ struct BackendTC : EvalBackend {
         return (int)std::max<int64_t>(1, std::min<int64_t>(best, max_splits));
     }
 
-    double lattice() const override { return level == 0 ? X_LATTICE_COARSE : X_LATTICE_FINE; }
-    double x_range() const override { return level == 0 ? X_RANGE_COARSE : X_RANGE_FINE; }
+    double lattice() const override { return level < 0 ? X_LATTICE_ROUGH : (level == 0 ? X_LATTICE_COARSE : X_LATTICE_FINE); }
+    double x_range() const override { return level <= 0 ? X_RANGE_COARSE : X_RANGE_FINE; }
+    int level_xl() const { return level < 0 ? 2 : (level == 0 ? 3 : 4); }
+    int level_nr() const { return level < 0 ? 1 : (level == 0 ? std::max(2, nR - 1) : nR); }
     // rounding noise of a gradient component: ~0.29 sqrt(K) wmax e^B / qmax(nr); e^B ~ 20 as a typical upper value
     double grad_noise() const override {
         const Histogram& h = *p.hist;
-        const int nr = level == 0 ? std::max(2, nR - 1) : nR;
-        return std::max(1e-9, 0.29 * std::sqrt(h.K_total) * h.wmax * 20.0 / r_qmax(nr));
+        return std::max(1e-9, 0.29 * std::sqrt(h.K_total) * h.wmax * 20.0 / r_qmax(level_nr()));
     }
     // level 0 needs |x| < 1 (checked by the quantiser: an overflow pins the backend to the fine level)
     bool coarse_overflow = false;
+    // levels: -1 rough, 0 coarse, 1 fine.  The rough level's single 8-bit residual plane is only accurate enough for
+    // near-uniform counts (the same condition that lets the fine level use 3 planes).
     bool set_level(int lv, cudaStream_t) override {
-        level = (lv == 0 && !coarse_overflow) ? 0 : 1;
+        if (lv < 0 && (coarse_overflow || nR != 3)) lv = 0;
+        level = (lv <= 0 && !coarse_overflow) ? lv : 1;
         return level == lv;
     }
     const int* device_flags() const override { return flags.p; }
@@ -1396,11 +1414,11 @@ struct BackendTC : EvalBackend {
 
     void eval(const double* x, bool want_grad, double* f_out, double* g_out, cudaStream_t st) override {
         const Histogram& h = *p.hist;
-        const int xl = level == 0 ? 3 : 4;
-        const int nr = level == 0 ? std::max(2, nR - 1) : nR;      // residual limbs of this pass
+        const int xl = level_xl();
+        const int nr = level_nr();                                  // residual digit planes of this pass
         const int n_nodes = act_idx ? n_act : p.Nn;                // slots of this pass
         const int pad1 = (int)round_up(n_nodes, NODE_TILE1), pad2 = (int)round_up(n_nodes, NODE_TILE2);
-        tc_quantize_x_kernel<<<pad1, 128, 0, st>>>(x, n_nodes, p.Fp, p.form, h.wmax, nr, xl, NODE_TILE1, 1.0 / lattice(), xl == 3 ? X3.p : X4.p,
+        tc_quantize_x_kernel<<<pad1, 128, 0, st>>>(x, n_nodes, p.Fp, p.form, h.wmax, nr, xl, NODE_TILE1, 1.0 / lattice(), xl == 2 ? X2.p : (xl == 3 ? X3.p : X4.p),
                                                    inv_dr.p, delta.p, flags.p, act_idx);
         GML_LAUNCHED();
         GML_CUDA(cudaMemsetAsync(fsum.p, 0, sizeof(double) * pad1, st));
@@ -1432,7 +1450,11 @@ struct BackendTC : EvalBackend {
             else GML_TC_ENERGY(FORM, true, XL, 4, MAPB, MAPBH);                             \
         } while (0)
         if (xl == 4) { if (rple) GML_TC_BY_NR(GML_B200_RPLE, 4, tmB, tmBh); else GML_TC_BY_NR(GML_B200_RISE, 4, tmB, tmBh); }
-        else { if (rple) GML_TC_BY_NR(GML_B200_RPLE, 3, tmB3, tmB3h); else GML_TC_BY_NR(GML_B200_RISE, 3, tmB3, tmB3h); }
+        else if (xl == 3) { if (rple) GML_TC_BY_NR(GML_B200_RPLE, 3, tmB3, tmB3h); else GML_TC_BY_NR(GML_B200_RISE, 3, tmB3, tmB3h); }
+        else {      // rough level: always one residual plane (objective-only passes have no residual at all)
+            if (rple) { if (want_grad) GML_TC_ENERGY(GML_B200_RPLE, true, 2, 1, tmB2, tmB2h); else GML_TC_ENERGY(GML_B200_RPLE, false, 2, 1, tmB2, tmB2h); }
+            else { if (want_grad) GML_TC_ENERGY(GML_B200_RISE, true, 2, 1, tmB2, tmB2h); else GML_TC_ENERGY(GML_B200_RISE, false, 2, 1, tmB2, tmB2h); }
+        }
 #undef GML_TC_BY_NR
 #undef GML_TC_ENERGY
         GML_LAUNCHED();
@@ -1451,7 +1473,7 @@ struct BackendTC : EvalBackend {
                 GML_LAUNCHED();
             }
             GradParams gp{};
-            const int ft = (nr == 2 && p.Fp % 256 == 0 && !std::getenv("GML_B200_GRAD_FT128")) ? 256 : 128;   // feature-tile width
+            const int ft = (nr <= 2 && p.Fp % 256 == 0 && !std::getenv("GML_B200_GRAD_FT128")) ? 256 : 128;   // feature-tile width
             gp.Fp = p.Fp; gp.m_tiles = pad2 / 128; gp.f_tiles = p.Fp / ft; gp.nR = nr;
             gp.r_rows_per_limb = Nn_pad2; gp.block_stride = stride; gp.sample_blocks = ceil_div(h.Kp / 128, stride); gp.G = G64.p;
             gp.dbg = ep.dbg;
@@ -1459,7 +1481,9 @@ struct BackendTC : EvalBackend {
             gp.n_splits = balanced_splits(tiles, n_sms, gp.sample_blocks);
             const int grid2 = std::min(n_sms, tiles * gp.n_splits);
             span_begin(1, st);
-            if (nr == 2 && ft == 256) tc_grad_kernel<2, 256><<<grid2, 192, grad_smem(2, 256), st>>>(tmRa, tmQ256, gp);
+            if (nr == 1 && ft == 256) tc_grad_kernel<1, 256><<<grid2, 192, grad_smem(1, 256), st>>>(tmRa, tmQ256, gp);
+            else if (nr == 1) tc_grad_kernel<1, 128><<<grid2, 192, grad_smem(1, 128), st>>>(tmRa, tmQ, gp);
+            else if (nr == 2 && ft == 256) tc_grad_kernel<2, 256><<<grid2, 192, grad_smem(2, 256), st>>>(tmRa, tmQ256, gp);
             else if (nr == 2) tc_grad_kernel<2, 128><<<grid2, 192, grad_smem(2, 128), st>>>(tmRa, tmQ, gp);
             else if (nr == 3) tc_grad_kernel<3, 128><<<grid2, 192, grad_smem(3, 128), st>>>(tmRa, tmQ, gp);
             else tc_grad_kernel<4, 128><<<grid2, 192, grad_smem(4, 128), st>>>(tmRa, tmQ, gp);

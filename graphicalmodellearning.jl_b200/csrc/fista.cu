@@ -332,12 +332,19 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
         // Precision levels: every node first runs with a 3-limb iterate (lattice 2^-20) and one residual limb less until
         // it reaches the tolerance or the resolution of that lattice, where it parks; when all have parked, the last
         // rounds run at full precision.  Coarse-lattice points are fine-lattice points: the switch only refreshes (f, G).
-        int level = (o.reserved[3] == 0 && user_tol <= 1e-4 && be->set_level(0, st)) ? 0 : 1;
+        // Levels of a lattice backend: -1 rough (cold starts only: 2-limb iterate on 2^-13, one 8-bit residual plane), 0 coarse,
+        // 1 fine.  A node runs on a level until it reaches the tolerance or the resolution of that level's lattice, parks,
+        // and when all have parked the solve moves one level up.
+        int level = 1;
+        if (o.reserved[3] == 0 && user_tol <= 1e-4) {
+            if (!prob.x0 && be->set_level(-1, st)) level = -1;
+            else if (be->set_level(0, st)) level = 0;
+        }
         be->set_level(1, st);
-        s.x_range = be->x_range();          // the clamp is the FINE level's range on both levels: the coarse level's own
-        if (level == 0) be->set_level(0, st);   // (smaller) range is watched by its quantiser, which raises device_flags()
+        s.x_range = be->x_range();          // the clamp is the FINE level's range on all levels: the lower levels' own
+        if (level != 1) be->set_level(level, st);   // (smaller) range is watched by the quantiser, which raises device_flags()
         auto sync_level = [&] {
-            s.fine = level; s.lattice = be->lattice(); s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
+            s.fine = level == 1 ? 1 : 0; s.lattice = be->lattice(); s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
             s.eps_g = be->grad_noise() * scale;
         };
         sync_level();
@@ -372,7 +379,7 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
         // gradient at 0 (= minus the pair correlations), see warmstart.cu.  One more pass, ~30 % fewer rounds expected.
         if (li == 0 && strides.size() == 1 && !prob.x0 && (o.reserved[7] & 1) != 0 && Nn == hist.N && prob.Q == hist.base.p &&
             prob.F == hist.N + 1) {
-            const double xmax = level == 0 ? 0.9 : 7.0;
+            const double xmax = level <= 0 ? 0.9 : 7.0;
             if (meanfield_start(G.p, Nn, Fp, prob.pen.p, xmax, s.lattice, Y.p, st)) {
                 GML_CUDA(cudaMemcpyAsync(r.x.p, Y.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
                 GML_CUDA(cudaMemcpyAsync(Z.p, Y.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -408,17 +415,19 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
             int h_flags = 0;
             GML_CUDA(cudaMemcpyAsync(&active, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             GML_CUDA(cudaMemcpyAsync(&h_gmax, gmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-            if (level == 0 && be->device_flags())
+            if (level < 1 && be->device_flags())
                 GML_CUDA(cudaMemcpyAsync(&h_flags, be->device_flags(), sizeof(int), cudaMemcpyDeviceToHost, st));
             GML_CUDA(cudaStreamSynchronize(st));       // the only host sync of the round
-            if (level == 0) {
-                const bool overflow = (h_flags & 2) != 0;           // some |x| reached 1: the 3-limb range is exhausted
+            if (level < 1) {
+                const bool overflow = (h_flags & 2) != 0;           // some |x| reached 1: the range of the lower levels is exhausted
                 if (overflow) be->note_coarse_overflow();
                 // every node has parked (reached the tolerance or the resolution of the coarse lattice): the stragglers
                 // finish on the coarse level in compacted -- cheap -- passes instead of dragging all nodes to the fine one
                 if (overflow || active == 0) {
-                    level = 1; be->set_level(1, st); sync_level();
-                    if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista: fine precision from round %d (gmap max %.3g, %d nodes still active%s)\n", it + 1, h_gmax, active, overflow ? ", coarse range overflow" : "");
+                    level = overflow ? 1 : level + 1;
+                    if (!be->set_level(level, st)) { level = 1; be->set_level(1, st); }
+                    sync_level();
+                    if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista: %s precision from round %d (gmap max %.3g, %d nodes still active%s)\n", level == 1 ? "fine" : "coarse", it + 1, h_gmax, active, overflow ? ", range overflow" : "");
                     whole_shard();
                     if (overflow) {
                         // restart from the last accepted iterate at full precision

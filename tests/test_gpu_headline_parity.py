@@ -42,48 +42,55 @@ def rel(a, b, form="RISE"):
 # (a) objective / gradient passes at headline shapes
 # ------------------------------------------------------------------------------------------------
 @functools.lru_cache(maxsize=None)
-def eval_case(n):
+def eval_case(n, uniform=False):
     rng = np.random.default_rng(1000 + n)
     k = 30_001                                                    # ragged: not a multiple of 128 (nor of 256)
     spins = rng.choice(np.array([-1, 1], dtype=np.int8), size=(n, k))
-    counts = rng.integers(1, 5, size=k).astype(np.float64)
+    counts = np.ones(k) if uniform else rng.integers(1, 5, size=k).astype(np.float64)
     nnz = 40.0 / n                                                # ~40 nonzeros per row, |x_u|_1 ~ 2
     x = rng.normal(size=(n, n + 1)) * 0.06 * (rng.random((n, n + 1)) < nnz)
-    x = np.clip(np.round(x * 2 ** 20) / 2 ** 20, -0.9, 0.9)       # on the coarse lattice (hence also on the fine one)
+    x = np.clip(np.round(x * 2 ** 13) / 2 ** 13, -0.9, 0.9)       # on the rough lattice (hence also on the coarse and fine ones)
     x[np.arange(n), np.arange(n)] = 0.0
     return counts, spins, x
 
 
 @functools.lru_cache(maxsize=None)
-def eval_oracle(n, form):
-    counts, spins, x = eval_case(n)
+def eval_oracle(n, form, uniform=False):
+    counts, spins, x = eval_case(n, uniform)
     return c.eval_pairwise(counts, spins, form, x)
 
 
 @functools.lru_cache(maxsize=None)
-def eval_session(n):
-    counts, spins, _ = eval_case(n)
+def eval_session(n, uniform=False):
+    counts, spins, _ = eval_case(n, uniform)
     return gml_b200.Session().upload(counts, np.ascontiguousarray(spins))
 
 
 @pytest.mark.parametrize("form", list(FORMS))
-@pytest.mark.parametrize("coarse", [True, False], ids=["coarse", "fine"])
+@pytest.mark.parametrize("level", ["rough", "coarse", "fine"])
 @pytest.mark.parametrize("n,kernel", [(300, "pair"), (300, "streaming"), (1000, "pair"), (1000, "streaming"), (1100, "streaming")])
-def test_passes_at_headline_shapes(monkeypatch, n, kernel, coarse, form):
+def test_passes_at_headline_shapes(monkeypatch, n, kernel, level, form):
     if kernel == "streaming":
         monkeypatch.setenv("GML_B200_NO_PAIR", "1")               # read when the backend is created (every eval call)
     else:
         monkeypatch.delenv("GML_B200_NO_PAIR", raising=False)
-    _, _, x = eval_case(n)
-    fr, gr = eval_oracle(n, form)
-    f, g = eval_session(n).eval_pairwise(FORMS[form](), x, "fista_tc", coarse=coarse)
+    uniform = level == "rough"            # the single 8-bit residual plane of the rough level needs near-uniform counts
+    _, _, x = eval_case(n, uniform)
+    fr, gr = eval_oracle(n, form, uniform)
+    f, g = eval_session(n, uniform).eval_pairwise(FORMS[form](), x, "fista_tc", coarse={"rough": "rough", "coarse": True, "fine": False}[level])
     ferr = np.abs(f - fr).max() / max(1.0, np.abs(fr).max())
     gerr = np.abs(g - gr).max() / max(1.0, np.abs(gr).max())
-    print(f"N={n} {kernel} {'coarse' if coarse else 'fine'} {form}: f err {ferr:.2e}, g err {gerr:.2e}")
-    # fp32 per-sample exp / log terms (ex2.approx: 2 ulp) bound the objective; the coarse level adds the rounding of the
-    # 16-bit residual digits to the gradient: ~0.3 sqrt(K) wmax e^B / 32000
+    print(f"N={n} {kernel} {level} {form}: f err {ferr:.2e}, g err {gerr:.2e}")
+    # fp32 per-sample exp / log terms (ex2.approx: 2 ulp) bound the objective; the lower levels add the rounding of their
+    # residual digits to the gradient: ~0.3 sqrt(K) wmax e^B / qmax with qmax = 120 (rough, 8 bits), 32000 (coarse, 16 bits)
     assert ferr <= 2e-6
-    assert gerr <= (2e-4 if coarse else 2e-5)
+    assert gerr <= {"rough": 2e-3, "coarse": 2e-4, "fine": 2e-5}[level]
+
+
+def test_rough_level_is_refused_for_strongly_weighted_histograms():
+    _, _, x = eval_case(300)
+    with pytest.raises(gml_b200.GMLB200Error):
+        eval_session(300).eval_pairwise(RISE(), x, "fista_tc", coarse="rough")
 
 
 def test_eval_rejects_points_outside_the_fixed_point_range():
