@@ -375,7 +375,7 @@ def run_b200(args):
     # where node problems follow partition-independent paths: src/GraphicalModelLearning.jl:161 has no cross-node dependency)
     multi_gpu_check = None
     if world > 1:
-        one_level = gml_b200.B200(solver=args.solver, tol=args.tol, device=local, coarse_level=False)
+        one_level = gml_b200.B200(solver=args.solver, tol=args.tol, device=local, coarse_level=False, warm_start=False)
         multi = learn_fn(one_level, False)
         ref0 = multi.clone()
         dist.broadcast(ref0, src=0)
@@ -385,7 +385,7 @@ def run_b200(args):
         tile_e = min(n, tile_b + 64)
         chk = gml_b200.Session(local).attach_device(counts.data_ptr(), spins.data_ptr(), k, n, k)
         tile_rows = torch.empty((tile_e - tile_b, n), dtype=torch.float64, device=dev)
-        chk.solve_pairwise_device(form, gml_b200.B200(solver=args.solver, tol=args.tol, device=local, coarse_level=False),
+        chk.solve_pairwise_device(form, gml_b200.B200(solver=args.solver, tol=args.tol, device=local, coarse_level=False, warm_start=False),
                                   tile_rows.data_ptr(), tile_b, tile_e)
         torch.cuda.synchronize()
         tile_err = torch.tensor([float((tile_rows - multi[tile_b:tile_e]).abs().max().item())], device=dev)
@@ -397,7 +397,7 @@ def run_b200(args):
                            "max_abs_diff_vs_single_rank_tile_resolve": float(tile_err.item()),
                            "max_abs_diff_two_level_vs_one_level_solve": float(two_level.item()),
                            "tile": "64 nodes per rank (a different tile on every rank), re-solved on ONE GPU from the full histogram; "
-                                   "both solves with coarse_level=False"}
+                                   "both solves cold and on one precision level (coarse_level=False, warm_start=False)"}
         assert mode == "node_sharded" or same.item() == 0.0, f"ranks disagree: {same.item()}"
         assert tile_err.item() <= 1e-6, f"multi-GPU solve differs from the single-rank re-solve: {tile_err.item()}"
 
@@ -509,7 +509,8 @@ def run_b200(args):
                            "partition": mode,
                            "arithmetic": "int8 tensor-core contractions with s32/s64 accumulation (exact), f32 per-sample epilogue, f64 solver state",
                            "tol": args.tol, "solver": args.solver, "l2_note": "inputs (10 GB int8 + 20-30 GB residual digits) exceed the 126 MB L2",
-                           "lambda": lam, "sampler_seconds": gen_s, "warm_start": bool(args.warm_start)},
+                           "lambda": lam, "sampler_seconds": gen_s,
+                           "warm_start": "library default (mean-field start for cold solves of all nodes; node shards start cold)" if args.warm_start is None else bool(args.warm_start)},
                 "learn_seconds": ms_step * 1e-3, "passes": {"fg": stats["n_fg_passes"], "f": stats["n_f_passes"], "iterations": stats["iterations"]},
                 "max_abs_coupling_error_vs_truth": recon_err, "max_residual": stats["max_residual"], "n_stalled": stats.get("n_stalled", 0),
                 "support": {"mean_nnz_per_row": float(nnz_row.mean()), "max_nnz_per_row": int(nnz_row.max()), "true_degree": 4},
@@ -630,7 +631,8 @@ def main():
     ap.add_argument("--verbose", type=int, default=0)
     ap.add_argument("--multilevel", action="store_true")
     ap.add_argument("--no-coarse", action="store_true")
-    ap.add_argument("--warm-start", action="store_true")
+    ap.add_argument("--warm-start", dest="warm_start", action="store_true", default=None)
+    ap.add_argument("--no-warm-start", dest="warm_start", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -87,7 +87,8 @@ class B200(GMLMethod):
     coarse_level: bool = True     # fista_tc: 3-limb iterate / one residual limb less while far from convergence
     devices: int = 1              # one-shot learn(): shard the nodes over this many GPUs from this process
     compaction: bool = True       # FISTA: restrict the passes to the nodes that are still active (parked / converged ones drop out)
-    warm_start: bool = False      # FISTA, full pairwise solves: start from the mean-field couplings (opt-in)
+    warm_start: Optional[bool] = None   # FISTA, cold solves of all nodes: start from the mean-field couplings (None = the
+                                        # library default: on for 128 <= N <= 2048; True forces it on, False switches it off)
     polish: bool = False          # FISTA solvers: finish every node with fp64 Newton on its identified support (exact L1 minimiser to ~1e-12)
     last_stats: dict = field(default_factory=dict, repr=False, compare=False)
 
@@ -107,7 +108,7 @@ class B200(GMLMethod):
         o.reserved[3] = 0 if self.coarse_level else 1
         o.reserved[4] = int(self.devices)
         o.reserved[6] = 0 if self.compaction else 1
-        o.reserved[7] = (1 if self.warm_start else 0) | (2 if self.polish else 0)
+        o.reserved[7] = (1 if self.warm_start else 0) | (2 if self.polish else 0) | (4 if self.warm_start is False else 0)
         return o
 
 

@@ -1344,6 +1344,26 @@ struct BackendTC : EvalBackend {
         return (int)std::max<int64_t>(1, std::min<int64_t>(best, max_splits));
     }
 
+    // Sample ranges of the CTA-pair energy kernel.  The pairs that work on one range (one per node tile) share its
+    // histogram tiles through L2 only while they stay within a few hundred blocks of each other; with one long range
+    // per pair (the wave-balanced minimum) they drift apart over thousands of steps and every P tile is fetched from
+    // HBM about twice (ncu: 20.1 GB read for a 10.2 GB histogram).  Ranges of at most ITEM_STEPS pair-steps bound the
+    // drift; the limb-tile reload per item (96 KB against 256 KB of histogram tiles per step) stays below 0.2 %.
+    static int pair_groups(int tiles, int n_pairs, int64_t pair_blocks) {
+        static const int item_steps = [] { const char* e = std::getenv("GML_B200_ITEM_STEPS"); return e ? std::max(1, std::atoi(e)) : 256; }();
+        const int64_t g_min = std::max<int64_t>(1, ceil_div(pair_blocks, item_steps));
+        const int wave = balanced_splits(tiles, n_pairs, pair_blocks);
+        if (g_min <= wave) return wave;
+        int64_t best = g_min; double best_eff = 0.0;
+        for (int64_t g = g_min; g < g_min + 2 * n_pairs && g <= pair_blocks; ++g) {
+            const int64_t items = (int64_t)tiles * g, waves = ceil_div(items, n_pairs);
+            const double eff = (double)items / (double)(waves * n_pairs);
+            if (eff > best_eff + 1e-9) { best = g; best_eff = eff; }
+            if (eff >= 0.985) break;
+        }
+        return (int)std::min<int64_t>(best, pair_blocks);
+    }
+
     double lattice() const override { return level < 0 ? X_LATTICE_ROUGH : (level == 0 ? X_LATTICE_COARSE : X_LATTICE_FINE); }
     double x_range() const override { return level <= 0 ? X_RANGE_COARSE : X_RANGE_FINE; }
     int level_xl() const { return level < 0 ? 2 : (level == 0 ? 3 : 4); }
@@ -1433,7 +1453,7 @@ struct BackendTC : EvalBackend {
 
         const bool pair = pair_ok && ep.sample_blocks >= 2;
         const int n_pairs = n_sms / 2;
-        ep.n_groups = pair ? balanced_splits(ep.n_tiles, n_pairs, (ep.sample_blocks + 1) / 2) : balanced_splits(ep.n_tiles, n_sms, ep.sample_blocks);
+        ep.n_groups = pair ? pair_groups(ep.n_tiles, n_pairs, (ep.sample_blocks + 1) / 2) : balanced_splits(ep.n_tiles, n_sms, ep.sample_blocks);
         const int grid1 = pair ? 2 * std::min(n_pairs, ep.n_tiles * ep.n_groups) : std::min(n_sms, ep.n_tiles * ep.n_groups);
         const bool rple = p.form == GML_B200_RPLE;
         span_begin(want_grad ? 0 : 2, st);

@@ -375,9 +375,13 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
         s.park_tol = s.tol;
         be->set_active(nullptr, 0, st);
         be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += pass_units();
-        // Opt-in (opts.reserved[7]): cold full pairwise solve -> start from the mean-field couplings read off the
-        // gradient at 0 (= minus the pair correlations), see warmstart.cu.  One more pass, ~30 % fewer rounds expected.
-        if (li == 0 && strides.size() == 1 && !prob.x0 && (o.reserved[7] & 1) != 0 && Nn == hist.N && prob.Q == hist.base.p &&
+        // Cold full pairwise solve -> start from the mean-field couplings read off the gradient at 0 (= minus the pair
+        // correlations), see warmstart.cu.  One more pass; measured at C3: 43 -> 35 rounds, learn() 1.29 -> 1.16 s.
+        // Default for cold solves of ALL nodes of a pairwise problem with 128 <= N <= 2048 (the N x N inverse is ~N tiny
+        // launches); opts.reserved[7] & 1 forces it on, & 4 switches it off.  Node shards (Nn < N) cannot use it: the
+        // inverse needs every row of the correlation matrix.
+        const bool mf_default = hist.N >= 128 && hist.N <= 2048 && (o.reserved[7] & 4) == 0;
+        if (li == 0 && strides.size() == 1 && !prob.x0 && ((o.reserved[7] & 1) != 0 || mf_default) && Nn == hist.N && prob.Q == hist.base.p &&
             prob.F == hist.N + 1) {
             const double xmax = level <= 0 ? 0.9 : 7.0;
             if (meanfield_start(G.p, Nn, Fp, prob.pen.p, xmax, s.lattice, Y.p, st)) {

@@ -150,12 +150,14 @@ __device__ __forceinline__ double barrier_phi(double x, double lam, double mu) {
     return lam * z - mu * log(2.0 * eps * z);
 }
 
-// One CTA (64 threads) per node: reduce partials, form the direction.
+// One CTA (128 threads >= NEWTON_MAX_F) per node: reduce partials, form the direction.
 // mode 0: exact (coordinate descent on the L1 quadratic model)
 // mode 1: barrier Newton (Cholesky)
 // mode 2: barrier warm start (moves exact zeros to their first-order barrier value), no direction
 // mode 3: objective only (obj[u] = f + lambda*|x_pen|_1)
-__global__ void __launch_bounds__(64) newton_direction_kernel(NewtonParams p, int form, int mode) {
+constexpr int ND = 128;        // threads of the direction kernel: one per feature (F <= NEWTON_MAX_F = 128)
+static_assert(ND >= NEWTON_MAX_F, "the direction kernel initialises one feature per thread");
+__global__ void __launch_bounds__(ND) newton_direction_kernel(NewtonParams p, int form, int mode) {
     const int u = blockIdx.x;
     if (p.conv[u] && mode < 2) return;
     const int F = p.F, tid = threadIdx.x;
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(64) newton_direction_kernel(NewtonParams p, in
     __shared__ uint8_t s_pen[NEWTON_MAX_F];
     const double lam = p.lambda;
 
-    for (int e = tid; e < P; e += 64) {
+    for (int e = tid; e < P; e += ND) {
         double s = 0.0;
         const double* src = p.part + (int64_t)u * p.chunks * P + e;
         for (int c = 0; c < p.chunks; ++c) s += src[(int64_t)c * P];
@@ -198,11 +200,11 @@ __global__ void __launch_bounds__(64) newton_direction_kernel(NewtonParams p, in
         __syncthreads();
         if (tid < F) g[tid] /= Z;
         __syncthreads();
-        for (int e = tid; e < F * F; e += 64) H[e] = H[e] / Z - g[e / F] * g[e % F];
+        for (int e = tid; e < F * F; e += ND) H[e] = H[e] / Z - g[e / F] * g[e % F];
         __syncthreads();
     }
     // fixed-zero coordinates drop out of the model
-    for (int e = tid; e < F * F; e += 64) {
+    for (int e = tid; e < F * F; e += ND) {
         const int a = e / F, b = e % F;
         if (s_pen[a] == PEN_ZERO || s_pen[b] == PEN_ZERO) H[e] = (a == b) ? 1.0 : 0.0;
     }
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(64) newton_direction_kernel(NewtonParams p, in
         }
         __syncthreads();
         const double l = H[j * F + j];
-        for (int i = j + 1 + tid; i < F; i += 64) {
+        for (int i = j + 1 + tid; i < F; i += ND) {
             double t = H[i * F + j];
             for (int k = 0; k < j; ++k) t -= H[i * F + k] * H[j * F + k];
             H[i * F + j] = t / l;
@@ -484,7 +486,7 @@ void solve_newton(const NodeProblem& prob, const gml_b200_opts& o, SolveResult& 
         for (int it = 0; it < max_iter; ++it) {
             ++total_iter;
             launch_accum(P, form, st); ++n_fg;
-            newton_direction_kernel<<<Nn, 64, dir_smem, st>>>(P, form, barrier ? 1 : 0);
+            newton_direction_kernel<<<Nn, ND, dir_smem, st>>>(P, form, barrier ? 1 : 0);
             GML_LAUNCHED();
             newton_linesearch_kernel<<<dim3(P.chunks, Nn), NT, 0, st>>>(P, form, NALPHA);
             GML_LAUNCHED(); ++n_f;
@@ -506,7 +508,7 @@ void solve_newton(const NodeProblem& prob, const gml_b200_opts& o, SolveResult& 
     if (o.barrier_mu > 0.0 && prob.lambda > 0.0) {
         GML_CUDA(cudaMemsetAsync(conv.p, 0, sizeof(int) * Nn, st));
         launch_accum(P, form, st); ++n_fg;
-        newton_direction_kernel<<<Nn, 64, dir_smem, st>>>(P, form, 2);
+        newton_direction_kernel<<<Nn, ND, dir_smem, st>>>(P, form, 2);
         GML_LAUNCHED();
         run_phase(1, 1e-15);
         unconverged += active;
@@ -514,7 +516,7 @@ void solve_newton(const NodeProblem& prob, const gml_b200_opts& o, SolveResult& 
     // final objective at the returned point
     GML_CUDA(cudaMemsetAsync(conv.p, 0, sizeof(int) * Nn, st));
     launch_accum(P, form, st); ++n_fg;
-    newton_direction_kernel<<<Nn, 64, dir_smem, st>>>(P, form, 3);
+    newton_direction_kernel<<<Nn, ND, dir_smem, st>>>(P, form, 3);
     GML_LAUNCHED();
 
     std::vector<double> hres(Nn);

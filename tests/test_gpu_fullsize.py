@@ -192,9 +192,10 @@ def test_node_chunking_when_memory_is_short(monkeypatch):
     spins = rng.choice(np.array([-1, 1], dtype=np.int8), size=(n, k))
     counts = np.ones(k)
     sess = gml_b200.Session(0).upload(counts, spins)
-    whole = sess.solve_pairwise(RISE(0.4, False), B200(coarse_level=False))
+    # (node chunks cannot use the mean-field start -- it needs the correlation rows of all nodes -- so the comparison runs cold)
+    whole = sess.solve_pairwise(RISE(0.4, False), B200(coarse_level=False, warm_start=False))
     monkeypatch.setenv("GML_B200_MEM_BUDGET_GB", "0.05")
-    m = B200(coarse_level=False)
+    m = B200(coarse_level=False, warm_start=False)
     chunked = sess.solve_pairwise(RISE(0.4, False), m)
     monkeypatch.delenv("GML_B200_MEM_BUDGET_GB")
     assert m.last_stats["n_fg_passes"] > 0

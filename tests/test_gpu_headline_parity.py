@@ -197,7 +197,7 @@ def test_c2_fixture_nodes_vs_oracle(c2, form, creg, nodes):
 
 def test_warm_start_changes_the_path_not_the_answer(c2):
     sess, _, _ = c2
-    cold = B200(tol=1e-7)
+    cold = B200(tol=1e-7, warm_start=False)
     warm = B200(tol=1e-7, warm_start=True)
     a = sess.solve_pairwise(RISE(0.4, False), cold)
     b = sess.solve_pairwise(RISE(0.4, False), warm)

@@ -72,8 +72,8 @@ def test_single_process_multi_device_learn():
     rng = np.random.default_rng(4)
     spins = rng.choice(np.array([-1, 1], dtype=np.int8), size=(n, 60_000))
     hist = np.concatenate([np.ones((60_000, 1)), spins.T.astype(np.float64)], axis=1)
-    one = gml_b200.learn(hist, gml_b200.RISE(0.4, True), gml_b200.B200(coarse_level=False))
-    m2 = gml_b200.B200(devices=2, coarse_level=False)
+    one = gml_b200.learn(hist, gml_b200.RISE(0.4, True), gml_b200.B200(coarse_level=False, warm_start=False))
+    m2 = gml_b200.B200(devices=2, coarse_level=False, warm_start=False)
     two = gml_b200.learn(hist, gml_b200.RISE(0.4, True), m2)
     assert np.abs(one - two).max() <= 1e-9
     assert np.array_equal(two, two.T)
