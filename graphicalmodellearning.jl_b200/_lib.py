@@ -26,7 +26,7 @@ EXPORTS = (
     "gml_b200_multibody_num_sym_keys", "gml_b200_threshold_device", "gml_b200_eval_pairwise", "gml_b200_bench_passes",
     "gml_b200_symmetrize_device",
     "gml_b200_sample_gibbs_device", "gml_b200_sample_gibbs_terms_device", "gml_b200_build_histogram_device",
-    "gml_b200_comm_unique_id", "gml_b200_comm_init", "gml_b200_comm_globalize_histogram",
+    "gml_b200_comm_unique_id", "gml_b200_comm_init", "gml_b200_comm_globalize_histogram", "gml_b200_comm_attach",
 )
 
 
@@ -119,6 +119,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.gml_b200_comm_unique_id.argtypes = [vp]
     lib.gml_b200_comm_init.argtypes = [vp, vp, c.c_int32, c.c_int32]
     lib.gml_b200_comm_globalize_histogram.argtypes = [vp]
+    lib.gml_b200_comm_attach.argtypes = [vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is c.c_int and name not in ("gml_b200_device_count",):

@@ -493,11 +493,26 @@ class Session:
         return dict(zip(("energy_full", "grad", "energy_obj", "full_pass_wall"), out.tolist()))
 
     # ---- sample-sharded mode -------------------------------------------------------------------------
-    def comm_init(self, group=None):
-        """Create the library's NCCL communicator over the ranks of a torch.distributed group (the 128-byte
-        unique id travels through torch.distributed), then make the resident histogram slice global."""
+    _comm_owners: dict = {}        # (device, id(group)) -> Session that owns the process's communicator for that group
+
+    def comm_init(self, group=None, reuse: bool = True):
+        """Join the library's NCCL communicator over the ranks of a torch.distributed group, then make the resident
+        histogram slice global.  The communicator is created ONCE per (device, group) and process -- the 128-byte unique
+        id travels through torch.distributed -- and later sessions attach to it (gml_b200_comm_attach): like a process
+        group, it is set-up cost, not part of a learn() call."""
         import torch
         import torch.distributed as dist
+        key = (self.device, id(group))
+        owner = Session._comm_owners.get(key) if reuse else None
+        if owner is not None and owner._h:
+            if owner is not self:
+                _lib.check(self._lib.gml_b200_comm_attach(self._h, owner._h))
+            _lib.check(self._lib.gml_b200_comm_globalize_histogram(self._h))
+            return self
+        if reuse:
+            owner = self if not self.N else Session(self.device)      # a data-less handle keeps the communicator alive
+        else:
+            owner = self
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         ident = (ctypes.c_uint8 * 128)()
         if rank == 0:
@@ -506,7 +521,11 @@ class Session:
         t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
         dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         ident = (ctypes.c_uint8 * 128)(*t.cpu().tolist())
-        _lib.check(self._lib.gml_b200_comm_init(self._h, ident, rank, world))
+        _lib.check(self._lib.gml_b200_comm_init(owner._h, ident, rank, world))
+        if reuse:
+            Session._comm_owners[key] = owner
+        if owner is not self:
+            _lib.check(self._lib.gml_b200_comm_attach(self._h, owner._h))
         _lib.check(self._lib.gml_b200_comm_globalize_histogram(self._h))
         return self
 

@@ -184,6 +184,7 @@ struct gml_b200_handle {
     Histogram hist;
     bool has_hist = false;
     Comm* comm = nullptr;      // sample-sharded mode
+    bool owns_comm = false;    // false: borrowed from another handle (gml_b200_comm_attach)
 };
 
 namespace {
@@ -432,7 +433,7 @@ int gml_b200_create(gml_b200_handle** out, int32_t device) {
 void gml_b200_destroy(gml_b200_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    comm_destroy(h->comm);
+    if (h->owns_comm) comm_destroy(h->comm);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -1202,9 +1203,19 @@ int gml_b200_comm_init(gml_b200_handle* h, const uint8_t* id128, int32_t rank, i
     return guarded([&] {
         GML_REQUIRE(h && id128, "null argument");
         GML_CUDA(cudaSetDevice(h->device));
-        comm_destroy(h->comm);
-        h->comm = nullptr;
+        if (h->owns_comm) comm_destroy(h->comm);
+        h->comm = nullptr; h->owns_comm = false;
         h->comm = comm_create(id128, rank, world);
+        h->owns_comm = true;
+    });
+}
+
+int gml_b200_comm_attach(gml_b200_handle* h, gml_b200_handle* owner) {
+    return guarded([&] {
+        GML_REQUIRE(h && owner && owner->comm, "needs a handle and an owner handle with a communicator");
+        GML_REQUIRE(h->device == owner->device, "the two handles must live on the same device");
+        if (h->owns_comm) comm_destroy(h->comm);
+        h->comm = owner->comm; h->owns_comm = false;
     });
 }
 

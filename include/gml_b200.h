@@ -41,7 +41,7 @@ extern "C" {
 
 /* solver selection */
 #define GML_B200_SOLVER_AUTO 0
-#define GML_B200_SOLVER_NEWTON 1   /* fp64 proximal-Newton, features <= 64 (small problems)        */
+#define GML_B200_SOLVER_NEWTON 1   /* fp64 proximal-Newton / barrier-Newton, features <= 128 (AUTO: <= 64) */
 #define GML_B200_SOLVER_FISTA_CC 2 /* batched FISTA, CUDA-core fp32 contractions                   */
 #define GML_B200_SOLVER_FISTA_TC 3 /* batched FISTA, tcgen05 (int8 limb) tensor-core contractions.  The iterate is a
                                       fixed-point number with |x| < 7.9; a node whose optimum lies beyond that range is
@@ -50,7 +50,8 @@ extern "C" {
 typedef struct gml_b200_opts {
     double tol;         /* stopping tolerance (max-norm of prox-gradient mapping / Newton step); default 1e-6 FISTA, 1e-12 Newton.
                            FISTA accepts a node that stalls at the gradient noise floor within 10*tol: see gml_b200_stats.n_stalled */
-    double barrier_mu;  /* 0 = exact L1 minimiser; > 0 = Ipopt-compatible log-barrier point at this mu (Newton solver only) */
+    double barrier_mu;  /* 0 = exact L1 minimiser; > 0 = Ipopt-compatible log-barrier point at this mu (Newton solver: at most
+                           128 features per node; AUTO selects it) */
     int32_t max_iter;   /* default 5000 */
     int32_t solver;     /* GML_B200_SOLVER_* */
     int32_t device;     /* CUDA device ordinal */
@@ -60,13 +61,18 @@ typedef struct gml_b200_opts {
     void* stream;       /* cudaStream_t to launch on; NULL = the handle's own stream */
     int32_t reserved[8]; /* reserved[0] != 0: time the contraction kernels with CUDA events (stats.reserved_d);
                             reserved[1] != 0: enable the multilevel (sample-subset) continuation of the FISTA solvers;
-                            reserved[2] != 0: sample-sharded solve (see gml_b200_comm_init);
-                            reserved[3] != 0: disable the coarse precision level of the tensor-core FISTA solver;
-                            reserved[4] > 1: gml_b200_learn_pairwise shards the nodes over that many devices
-                            (device, device+1, ...) from this one process, one host thread per device;
-                            reserved[5] == 1: gml_b200_bench_passes times the coarse precision level;
+                            reserved[2] == 1: sample-sharded solve (see gml_b200_comm_init); == 2: force node shards in the
+                            multi-device one-shot calls;
+                            reserved[3] != 0: disable the lower precision levels of the tensor-core FISTA solver;
+                            reserved[4] > 1: the one-shot calls split the work over that many devices (device, device+1, ...)
+                            from this one process, one host thread per device: histogram rows when every device keeps
+                            >= 65536 of them (sample-sharded solve), node shards otherwise;
+                            reserved[5]: gml_b200_eval_pairwise / gml_b200_bench_passes run on the coarse (1) or rough (2)
+                            precision level;
                             reserved[6] != 0: disable the active-set compaction of the FISTA passes;
-                            reserved[7] != 0: (experimental) mean-field warm start of cold full pairwise FISTA solves */
+                            reserved[7]: bit 0 force the mean-field warm start of cold full pairwise FISTA solves (default: on
+                            for 128 <= N <= 2048), bit 2 switch it off, bit 1 finish every node with fp64 Newton on its
+                            identified support (exact L1 minimiser to ~1e-10 for any number of features) */
 } gml_b200_opts;
 
 typedef struct gml_b200_stats {
@@ -195,7 +201,9 @@ int gml_b200_threshold_device(double* d_theta, int32_t N, double tau, int64_t* o
 /* Objective and gradient of the smooth part f_u (src/GraphicalModelLearning.jl:170 / 279 / 317) for all nodes of
  * the shard at a caller-supplied point.  x, g_out: (node_end-node_begin) x (N+1) row-major host arrays, feature
  * order = couplings to spins 0..N-1 (the self entry is ignored / returns 0), then the local field.  `solver`
- * selects the contraction backend (GML_B200_SOLVER_FISTA_CC or _TC; the TC backend rounds x to its 2^-24 lattice). */
+ * selects the contraction backend (GML_B200_SOLVER_FISTA_CC or _TC; the TC backend rounds x to the lattice of the
+ * precision level chosen by opts->reserved[5]: 2^-24 fine, 2^-20 coarse, 2^-13 rough; a coefficient outside the level's
+ * range (|x| < 7.9 fine, < 0.99 below) is GML_B200_EINVAL, never clamped). */
 int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b200_opts* opts, const double* x,
                            double* f_out, double* g_out /* nullable */);
 
@@ -232,6 +240,9 @@ int gml_b200_sample_gibbs_terms_device(int32_t device, int32_t N, int32_t order,
 int gml_b200_comm_unique_id(uint8_t* out128);
 int gml_b200_comm_init(gml_b200_handle* h, const uint8_t* id128, int32_t rank, int32_t world);
 int gml_b200_comm_globalize_histogram(gml_b200_handle* h);
+/* Borrow the communicator of `owner` (same device, same process; `owner` must outlive h's last solve): creating an NCCL
+ * communicator costs 0.1-1 s, a process makes ONE and every later histogram / learn() call attaches to it. */
+int gml_b200_comm_attach(gml_b200_handle* h, gml_b200_handle* owner);
 
 /* ---- histogram builder: replaces the host `countmap` of src/sampling.jl:52-54 -----------------
  * d_samples: M raw samples, int8 spin-major [N x ld] in device memory, N <= 64.  Writes the K distinct
