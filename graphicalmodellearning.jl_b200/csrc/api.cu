@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 namespace gml {
@@ -934,8 +935,16 @@ static int learn_pairwise_multi_device_samples(const HostSource& src, int64_t K,
                                                int32_t formulation, double lambda, int32_t symmetrize, const gml_b200_opts& base,
                                                int n_dev, double* out_theta, double* out_objective, gml_b200_stats* stats) {
     const double t0 = now_ms();
+    // One communicator per (first device, device count) and process: ncclCommInitRank costs 0.1-1 s, a learn() call ~1 s.
+    // The per-rank communicators are created by the first call and reused by the host threads of every later call.
+    static std::mutex cache_mutex;
+    static std::map<std::pair<int, int>, std::vector<Comm*>> comm_cache;
+    std::lock_guard<std::mutex> cache_lock(cache_mutex);      // also serialises concurrent multi-device calls on these devices
+    std::vector<Comm*>& cached = comm_cache[std::make_pair((int)base.device, n_dev)];
+    const bool have_comm = (int)cached.size() == n_dev;
     uint8_t ident[128];
-    if (gml_b200_comm_unique_id(ident) != GML_B200_OK) return -1;      // no NCCL: the caller falls back to node shards
+    if (!have_comm && gml_b200_comm_unique_id(ident) != GML_B200_OK) { comm_cache.erase(std::make_pair((int)base.device, n_dev)); return -1; }   // no NCCL: node shards
+    if (!have_comm) cached.assign(n_dev, nullptr);
     std::vector<int> rcs(n_dev, GML_B200_OK);
     std::vector<std::string> errs(n_dev);
     std::vector<gml_b200_stats> sts(n_dev);
@@ -954,7 +963,12 @@ static int learn_pairwise_multi_device_samples(const HostSource& src, int64_t K,
             int rc = gml_b200_create(&h, o.device);
             if (rc == GML_B200_OK) rc = src.upload(h, k0, k1, N, &up);
             // every thread must reach the communicator set-up, also after a failed upload (the others would wait for ever)
-            const int rc_comm = h ? gml_b200_comm_init(h, ident, r, n_dev) : GML_B200_ECUDA;
+            int rc_comm = GML_B200_ECUDA;
+            if (h && have_comm) { h->comm = cached[r]; h->owns_comm = false; rc_comm = GML_B200_OK; }
+            else if (h) {
+                rc_comm = gml_b200_comm_init(h, ident, r, n_dev);
+                if (rc_comm == GML_B200_OK) { cached[r] = h->comm; h->owns_comm = false; }      // the cache owns it from now on
+            }
             if (rc == GML_B200_OK) rc = rc_comm;
             if (rc_comm == GML_B200_OK) {       // leave together if any device failed so far
                 int agreed = rc;
@@ -979,6 +993,9 @@ static int learn_pairwise_multi_device_samples(const HostSource& src, int64_t K,
             gml_b200_destroy(h);
         });
     for (auto& t : threads) t.join();
+    if (!have_comm)
+        for (int r = 0; r < n_dev; ++r)
+            if (!cached[r]) { comm_cache.erase(std::make_pair((int)base.device, n_dev)); break; }      // set-up failed on some device: retry next call
     int rc = GML_B200_OK;
     for (int r = 0; r < n_dev; ++r)
         if (rcs[r] != GML_B200_OK && (rc == GML_B200_OK || rc == GML_B200_ENOTCONV)) { rc = rcs[r]; set_error("device " + std::to_string(base.device + r) + ": " + errs[r]); }
