@@ -84,7 +84,8 @@ class B200(GMLMethod):
     profile: bool = False         # time the contraction kernels with CUDA events (stats energy_*_ms / grad_ms)
     multilevel: bool = False      # FISTA: solve on strided sample subsets first (warm starts); opt-in
     sample_sharded: bool = False  # histogram rows split over ranks, NCCL all-reduce per pass (Session.comm_init)
-    coarse_level: bool = True     # fista_tc: 3-limb iterate / one residual limb less while far from convergence
+    coarse_level: object = True   # fista_tc: 3-limb iterate / one residual limb less while far from convergence ("rough": also the
+                                  # experimental 2-limb / 8-bit level first)
     devices: int = 1              # one-shot learn(): shard the nodes over this many GPUs from this process
     compaction: bool = True       # FISTA: restrict the passes to the nodes that are still active (parked / converged ones drop out)
     warm_start: Optional[bool] = None   # FISTA, cold solves of all nodes: start from the mean-field couplings (None = the
@@ -105,7 +106,7 @@ class B200(GMLMethod):
         o.reserved[0] = 1 if self.profile else 0
         o.reserved[1] = 1 if self.multilevel else 0
         o.reserved[2] = 1 if self.sample_sharded else 0
-        o.reserved[3] = 0 if self.coarse_level else 1
+        o.reserved[3] = 2 if self.coarse_level == "rough" else (0 if self.coarse_level else 1)
         o.reserved[4] = int(self.devices)
         o.reserved[6] = 0 if self.compaction else 1
         o.reserved[7] = (1 if self.warm_start else 0) | (2 if self.polish else 0) | (4 if self.warm_start is False else 0)

@@ -1378,8 +1378,9 @@ struct BackendTC : EvalBackend {
     // levels: -1 rough, 0 coarse, 1 fine.  The rough level's single 8-bit residual plane is only accurate enough for
     // near-uniform counts (the same condition that lets the fine level use 3 planes).
     bool set_level(int lv, cudaStream_t) override {
-        if (lv < 0 && (coarse_overflow || nR != 3)) lv = 0;
-        level = (lv <= 0 && !coarse_overflow) ? lv : 1;
+        int take = lv;
+        if (take < 0 && nR != 3) take = 0;
+        level = (take <= 0 && !coarse_overflow) ? take : 1;
         return level == lv;
     }
     const int* device_flags() const override { return flags.p; }

@@ -332,12 +332,15 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
         // Precision levels: every node first runs with a 3-limb iterate (lattice 2^-20) and one residual limb less until
         // it reaches the tolerance or the resolution of that lattice, where it parks; when all have parked, the last
         // rounds run at full precision.  Coarse-lattice points are fine-lattice points: the switch only refreshes (f, G).
-        // Levels of a lattice backend: -1 rough (cold starts only: 2-limb iterate on 2^-13, one 8-bit residual plane), 0 coarse,
-        // 1 fine.  A node runs on a level until it reaches the tolerance or the resolution of that level's lattice, parks,
-        // and when all have parked the solve moves one level up.
+        // Levels of a lattice backend: 0 coarse, 1 fine; -1 rough (2-limb iterate on 2^-13, one 8-bit residual plane: 3 executed
+        // GEMM units per pass instead of 5) only on request (opts.reserved[3] == 2).  A node runs on a level until it reaches
+        // the tolerance or the resolution of that level's lattice, parks, and when all have parked the solve moves one level
+        // up.  The rough level is NOT part of the default path: its kernels are exact (parity-tested like the others), but
+        // snapping the iterates to a 1.2e-4 lattice keeps triggering the gradient-scheme restart, FISTA degenerates to ISTA
+        // and the solve needs 93 rounds instead of 35 at C3 (2.41 s against 1.16 s; profiles/r2_rough_level_experiment.json).
         int level = 1;
-        if (o.reserved[3] == 0 && user_tol <= 1e-4) {
-            if (!prob.x0 && be->set_level(-1, st)) level = -1;
+        if ((o.reserved[3] == 0 || o.reserved[3] == 2) && user_tol <= 1e-4) {
+            if (o.reserved[3] == 2 && !prob.x0 && be->set_level(-1, st)) level = -1;
             else if (be->set_level(0, st)) level = 0;
         }
         be->set_level(1, st);

@@ -63,7 +63,8 @@ typedef struct gml_b200_opts {
                             reserved[1] != 0: enable the multilevel (sample-subset) continuation of the FISTA solvers;
                             reserved[2] == 1: sample-sharded solve (see gml_b200_comm_init); == 2: force node shards in the
                             multi-device one-shot calls;
-                            reserved[3] != 0: disable the lower precision levels of the tensor-core FISTA solver;
+                            reserved[3] == 1: disable the lower precision levels of the tensor-core FISTA solver; == 2: also run
+                            the experimental rough level first (measured slower: see DESIGN.md);
                             reserved[4] > 1: the one-shot calls split the work over that many devices (device, device+1, ...)
                             from this one process, one host thread per device: histogram rows when every device keeps
                             >= 65536 of them (sample-sharded solve), node shards otherwise;
