@@ -178,9 +178,6 @@ struct EvalBackend {
     // precision level of the following passes: 0 = coarse (cheaper, coarser lattice), 1 = fine.  Returns
     // whether the requested level was taken (backends without levels always run fine).
     virtual bool set_level(int lv, cudaStream_t) { return lv == 1; }
-    // Coarse level only: evaluate the residuals with `planes` digit planes instead of the level's default (0 = default).
-    // Returns false when the backend has no such choice (the call is then a no-op).
-    virtual bool set_residual_planes(int /*planes*/) { return false; }
     // device word whose bit 1 is raised when the coarse level's range overflowed (nullptr: no such condition);
     // the driver reads it together with its own per-round counters to keep ONE host sync per round
     virtual const int* device_flags() const { return nullptr; }

@@ -1307,12 +1307,10 @@ struct BackendTC : EvalBackend {
     void configure() {
 #define GML_TC_SET(FORM, XL)                                               \
         set_smem(tc_energy_kernel<FORM, false, XL, 2>, E_SMEM);                \
-        set_smem(tc_energy_kernel<FORM, true, XL, 1>, E_SMEM);                 \
         set_smem(tc_energy_kernel<FORM, true, XL, 2>, E_SMEM);                 \
         set_smem(tc_energy_kernel<FORM, true, XL, 3>, E_SMEM);                 \
         set_smem(tc_energy_kernel<FORM, true, XL, 4>, E_SMEM);                 \
         set_smem(tc_energy_pair_kernel<FORM, false, XL, 2>, e2_smem(XL));           \
-        set_smem(tc_energy_pair_kernel<FORM, true, XL, 1>, e2_smem(XL));            \
         set_smem(tc_energy_pair_kernel<FORM, true, XL, 2>, e2_smem(XL));            \
         set_smem(tc_energy_pair_kernel<FORM, true, XL, 3>, e2_smem(XL));            \
         set_smem(tc_energy_pair_kernel<FORM, true, XL, 4>, e2_smem(XL))
@@ -1369,15 +1367,7 @@ struct BackendTC : EvalBackend {
     double lattice() const override { return level < 0 ? X_LATTICE_ROUGH : (level == 0 ? X_LATTICE_COARSE : X_LATTICE_FINE); }
     double x_range() const override { return level <= 0 ? X_RANGE_COARSE : X_RANGE_FINE; }
     int level_xl() const { return level < 0 ? 2 : (level == 0 ? 3 : 4); }
-    int planes_override = 0;            // coarse level: residual digit planes of the early rounds (set_residual_planes)
-    int level_nr() const { return level < 0 ? 1 : (level == 0 ? (planes_override ? planes_override : std::max(2, nR - 1)) : nR); }
-    // One 8-bit plane halves the gradient GEMM of the coarse level (ncu: 12.7 -> 7.3 ms at C3); its rounding noise
-    // (~5e-6 per gradient component at C3) only suits rounds whose gradient mapping is still >> 1e-5 and near-uniform counts.
-    bool set_residual_planes(int planes) override {
-        if (planes != 0 && (planes != 1 || nR != 3)) return false;
-        planes_override = planes;
-        return true;
-    }
+    int level_nr() const { return level < 0 ? 1 : (level == 0 ? std::max(2, nR - 1) : nR); }
     // rounding noise of a gradient component: ~0.29 sqrt(K) wmax e^B / qmax(nr); e^B ~ 20 as a typical upper value
     double grad_noise() const override {
         const Histogram& h = *p.hist;
@@ -1476,7 +1466,6 @@ struct BackendTC : EvalBackend {
 #define GML_TC_BY_NR(FORM, XL, MAPB, MAPBH)                                                 \
         do {                                                                                \
             if (!want_grad) GML_TC_ENERGY(FORM, false, XL, 2, MAPB, MAPBH);                 \
-            else if (nr == 1) GML_TC_ENERGY(FORM, true, XL, 1, MAPB, MAPBH);                \
             else if (nr == 2) GML_TC_ENERGY(FORM, true, XL, 2, MAPB, MAPBH);                \
             else if (nr == 3) GML_TC_ENERGY(FORM, true, XL, 3, MAPB, MAPBH);                \
             else GML_TC_ENERGY(FORM, true, XL, 4, MAPB, MAPBH);                             \

