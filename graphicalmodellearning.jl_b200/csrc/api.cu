@@ -249,6 +249,7 @@ void solve_pairwise_rows_one(gml_b200_handle* h, int formulation, double lambda,
     pairwise_setup_kernel<<<p.Nn, 128, 0, st>>>(N, p.Fp, nb, p.Nn, p.spin_row.p, p.pen.p);
     GML_LAUNCHED();
     SolveResult r;
+    r.want_objective = d_obj != nullptr;      // the objective at the returned point costs one more pass over the histogram
     int solver_used = 0;
     if (warm && warm->p) p.x0 = warm->p;
     run_solver(p, o, r, solver_used, st);
@@ -551,7 +552,7 @@ int gml_b200_solve_pairwise(gml_b200_handle* h, int32_t formulation, double lamb
         rows.alloc((size_t)Nn * N); obj.alloc(Nn);
         int rc = GML_B200_OK;
         try {
-            solve_pairwise_rows(h, formulation, lambda, o, nb, ne, rows.p, obj.p, stats, st, t0);
+            solve_pairwise_rows(h, formulation, lambda, o, nb, ne, rows.p, out_objective ? obj.p : nullptr, stats, st, t0);
         } catch (const CudaError& e) {
             if (e.code != GML_B200_ENOTCONV) throw;
             rc = e.code;   // still hand back the best iterate, then report

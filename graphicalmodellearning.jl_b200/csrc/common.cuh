@@ -130,6 +130,7 @@ struct SolveResult {
     int n_unpolished = 0;     // support polish: nodes whose support exceeded the reduced solver's 64 features (FISTA point kept)
     DevBuf<double> grad;      // [Nn x Fp] gradient of the smooth part at x (filled by solve_fista when want_grad_at_x)
     bool want_grad_at_x = false;
+    bool want_objective = true;   // false: the FISTA driver skips the final objective pass (`objective` is then not filled)
     double max_residual = 0.0;
 };
 

@@ -238,9 +238,17 @@ static int solve_exact(const node_problem* p, const uint8_t* pen, double lam, do
     double* Hd = malloc(sizeof(double) * F);
     double* xn = malloc(sizeof(double) * F);
     int it = 0;
+    double F_prev = INFINITY, step_prev = INFINITY;
+    int idle = 0;
     for (; it < max_outer; ++it) {
         double f = eval_fgh(p, x, g, H, row); ++*n_fgh;
         double Fx = f + lam * l1_pen(x, pen, F);
+        /* A coordinate that sits on the activation threshold to rounding keeps flipping between 0 and ~1e-11: the step
+         * never drops below tol although the objective has stopped moving.  Stop there (the point is converged to the
+         * precision float64 sums over K rows can resolve) instead of spending all max_outer Hessian sweeps. */
+        idle = (it > 1 && step_prev < 1e-9 && fabs(F_prev - Fx) <= 1e-13 * fmax(fabs(Fx), 1.0)) ? idle + 1 : 0;
+        if (idle >= 4) break;
+        F_prev = Fx;
         memset(d, 0, sizeof(double) * F);
         memset(Hd, 0, sizeof(double) * F);
         for (int sweep = 0; sweep < 10000; ++sweep) {
@@ -266,6 +274,7 @@ static int solve_exact(const node_problem* p, const uint8_t* pen, double lam, do
         }
         double step = 0.0;
         for (int j = 0; j < F; ++j) if (fabs(d[j]) > step) step = fabs(d[j]);
+        step_prev = step;
         if (step < tol) { for (int j = 0; j < F; ++j) x[j] += d[j]; ++it; break; }
         double gd = 0.0;
         for (int j = 0; j < F; ++j) { gd += g[j] * d[j]; xn[j] = x[j] + d[j]; }
