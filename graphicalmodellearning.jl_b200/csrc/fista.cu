@@ -34,6 +34,8 @@ struct FistaState {
     const uint8_t* pen;
     double *X, *Z, *Y, *Yn, *G, *Gn;
     double *fY, *fYn, *L, *t, *tn, *q, *c, *gmap, *obj;
+    double* gtrue;    // gradient-mapping norm of the UNSNAPPED prox point (what the stopping rule is about; gmap is the snapped one)
+    int coarse_retire;   // 1: nodes may retire on the coarse level (its gradient noise is far below tol)
     double* best;     // smallest gradient-mapping norm seen
     int *stall, *streak;
     int* status;      // 0 active, 1 converged, 2 stalled at the gradient noise floor, 3 parked (done with the coarse level),
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
     __shared__ double red[4];
     const double L = s.L[u], thr = s.lambda / L;
     const int64_t o = (int64_t)u * s.Fp;
-    double dm = 0.0, r = 0.0;
+    double dm = 0.0, r = 0.0, dm_true = 0.0;
     bool clamped = false;
     for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
         const uint8_t pc = s.pen[o + f];
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
         if (pc != PEN_ZERO) {
             z = y - g / L;
             if (pc == PEN_L1) { const double a = fabs(z) - thr; z = a > 0.0 ? copysign(a, z) : 0.0; }
+            dm_true = fmax(dm_true, fabs(z - y));
             z = snap_flag(z, s, clamped);
         }
         s.Z[o + f] = z;
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
         r += (y - z) * (z - s.X[o + f]);          // gradient-scheme adaptive restart: <Y - Z, Z - X> > 0
     }
     dm = block_max(dm, red);
+    dm_true = block_max(dm_true, red);
     r = block_sum(r, red);
     const double t = s.t[u];
     const bool restart = r > 0.0;
@@ -116,7 +120,8 @@ __global__ void __launch_bounds__(128) fista_trial_kernel(FistaState s) {
     if (threadIdx.x == 0) {
         s.q[u] = q1 + 0.5 * L * q2;
         s.c[u] = 0.5 * L * q2;
-        s.gmap[u] = L * dm;          // max-norm of the prox-gradient mapping at Y
+        s.gmap[u] = L * dm;          // max-norm of the prox-gradient mapping at Y (to the snapped prox point)
+        s.gtrue[u] = L * dm_true;    // ... to the exact prox point
         s.tn[u] = tn;
         atomicMax(s.gmax, (unsigned long long)__double_as_longlong(L * dm));   // non-negative doubles order like their bits
     }
@@ -145,6 +150,24 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
     if (conv) {
         for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) s.X[o + f] = s.Z[o + f];
         if (threadIdx.x == 0) s.status[u] = 1;
+        return;
+    }
+    // Coarse level, when its gradient noise is far below the tolerance (16-bit residuals: ~6e-8 at C3): the stopping rule
+    // -- prox-gradient mapping at Y <= tol -- is evaluated with the EXACT prox point; a node that meets it is done and
+    // returns that point (not its snap to the coarse lattice).  Only nodes that the 2^-20 lattice keeps above tol (their Y
+    // cannot get close enough to the fixed point) go on to the fine level.
+    if (!s.fine && s.coarse_retire && s.gtrue[u] <= s.tol && !was_clamped) {
+        const double Lu = s.L[u], thr = s.lambda / Lu;
+        for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
+            const uint8_t pc = s.pen[o + f];
+            double z = 0.0;
+            if (pc != PEN_ZERO) {
+                z = s.Y[o + f] - s.G[o + f] / Lu;
+                if (pc == PEN_L1) { const double a = fabs(z) - thr; z = a > 0.0 ? copysign(a, z) : 0.0; }
+            }
+            s.X[o + f] = z;
+        }
+        if (threadIdx.x == 0) { s.status[u] = 1; s.gmap[u] = s.gtrue[u]; }
         return;
     }
     // Coarse level: nothing retires, but a node that has reached the resolution of the coarse lattice stops taking
@@ -270,7 +293,7 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
                                                                         : make_backend_cc(prob, st));
     be->set_profiling(o.reserved[0] != 0);
     const size_t nx = (size_t)Nn * Fp;
-    DevBuf<double> Z, Y, Yn, G, Gn, fY, fYn, L, t, tn, q, c, gmap, best;
+    DevBuf<double> Z, Y, Yn, G, Gn, fY, fYn, L, t, tn, q, c, gmap, best, gtrue;
     DevBuf<int> status, n_active, stall, streak, clamped;
     DevBuf<unsigned long long> gmax;
     DevBuf<int> act_idx;     // compacted list of the active nodes
@@ -278,6 +301,7 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
     r.x.alloc(nx); r.objective.alloc(Nn);
     Z.alloc(nx); Y.alloc(nx); Yn.alloc(nx); G.alloc(nx); Gn.alloc(nx);
     fY.alloc(Nn); fYn.alloc(Nn); L.alloc(Nn); t.alloc(Nn); tn.alloc(Nn); q.alloc(Nn); c.alloc(Nn); gmap.alloc(Nn);
+    gtrue.alloc(Nn);
     status.alloc(Nn); n_active.alloc(1); best.alloc(Nn); stall.alloc(Nn); streak.alloc(Nn); gmax.alloc(1); clamped.alloc(Nn);
     if (prob.x0) GML_CUDA(cudaMemcpyAsync(r.x.p, prob.x0, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
     else GML_CUDA(cudaMemsetAsync(r.x.p, 0, nx * sizeof(double), st));
@@ -290,7 +314,7 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
     s.lattice = be->lattice();
     s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
     s.eps_f = 1e-6;   // generous upper bound of the evaluation noise of f
-    s.best = best.p; s.stall = stall.p; s.streak = streak.p; s.clamped = clamped.p;
+    s.best = best.p; s.stall = stall.p; s.streak = streak.p; s.clamped = clamped.p; s.gtrue = gtrue.p;
     s.pen = prob.pen.p;
     s.X = r.x.p; s.Z = Z.p; s.Y = Y.p; s.Yn = Yn.p; s.G = G.p; s.Gn = Gn.p;
     s.fY = fY.p; s.fYn = fYn.p; s.L = L.p; s.t = t.p; s.tn = tn.p; s.q = q.p; s.c = c.p; s.gmap = gmap.p;
@@ -353,6 +377,8 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
         auto sync_level = [&] {
             s.fine = level == 1 ? 1 : 0; s.lattice = be->lattice(); s.lattice_inv = s.lattice > 0 ? 1.0 / s.lattice : 0.0;
             s.eps_g = be->grad_noise() * scale;
+            // retirement on the coarse level needs its gradient noise (conservative estimate) well below the tolerance
+            s.coarse_retire = (level == 0 && s.eps_g <= 0.25 * s.tol) ? 1 : 0;
         };
         sync_level();
         if (prob.x0 && li == 0 && s.lattice > 0.0) {
