@@ -1364,8 +1364,18 @@ struct BackendTC : EvalBackend {
         return (int)std::min<int64_t>(best, pair_blocks);
     }
 
-    double lattice() const override { return level < 0 ? X_LATTICE_ROUGH : (level == 0 ? X_LATTICE_COARSE : X_LATTICE_FINE); }
-    double x_range() const override { return level <= 0 ? X_RANGE_COARSE : X_RANGE_FINE; }
+    // The coarse level's 3 limbs hold |q| <= 1040000 lattice units: lattice 2^-20 covers |x| < 0.99 (the default, safe for a
+    // cold start), 2^-21 covers |x| < 0.495, ...  A finer coarse lattice lets nodes meet the tolerance on the coarse level
+    // (the snapped iteration stops within half a lattice unit of its fixed point: a gradient mapping of up to L * lattice / 2).
+    double coarse_lattice = X_LATTICE_COARSE;
+    double set_coarse_range(double need) override {
+        double lat = X_LATTICE_COARSE;
+        for (int i = 0; i < 2 && X_RANGE_COARSE * (lat * 0.5 / X_LATTICE_COARSE) >= need; ++i) lat *= 0.5;
+        coarse_lattice = lat;
+        return lat;
+    }
+    double lattice() const override { return level < 0 ? X_LATTICE_ROUGH : (level == 0 ? coarse_lattice : X_LATTICE_FINE); }
+    double x_range() const override { return level < 0 ? X_RANGE_COARSE : (level == 0 ? X_RANGE_COARSE * (coarse_lattice / X_LATTICE_COARSE) : X_RANGE_FINE); }
     int level_xl() const { return level < 0 ? 2 : (level == 0 ? 3 : 4); }
     int level_nr() const { return level < 0 ? 1 : (level == 0 ? std::max(2, nR - 1) : nR); }
     // rounding noise of a gradient component: ~0.29 sqrt(K) wmax e^B / qmax(nr); e^B ~ 20 as a typical upper value
