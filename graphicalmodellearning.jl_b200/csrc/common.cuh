@@ -179,9 +179,6 @@ struct EvalBackend {
     // precision level of the following passes: 0 = coarse (cheaper, coarser lattice), 1 = fine.  Returns
     // whether the requested level was taken (backends without levels always run fine).
     virtual bool set_level(int lv, cudaStream_t) { return lv == 1; }
-    // Coarse level: pick the finest lattice whose range still covers |x| <= need (3 limbs hold a fixed number of lattice
-    // units, so range and resolution trade off).  Returns the lattice now in force for the coarse level (0: no such level).
-    virtual double set_coarse_range(double /*need*/) { return 0.0; }
     // device word whose bit 1 is raised when the coarse level's range overflowed (nullptr: no such condition);
     // the driver reads it together with its own per-round counters to keep ONE host sync per round
     virtual const int* device_flags() const { return nullptr; }

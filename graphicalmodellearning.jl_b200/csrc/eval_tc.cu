@@ -3,7 +3,7 @@
 // by TMA into 128B-swizzled shared memory), in EXACT fixed-point arithmetic:
 //
 //   * the iterate lives on the lattice 2^-24 (the FISTA driver snaps to it), so x = q * 2^-24 with
-//     |q| < 2^27, split into 4 balanced base-128 int8 limbs.  The energy contraction
+//     |q| < 2^27, split into 4 balanced base-256 int8 limbs (digits in [-128, 127]).  The energy contraction
 //         E[k,u] = sum_f S[k,f] * x_u[f]            (S = +-1 features, int8)
 //     is then four int8 GEMM column groups with int32 accumulation -- no rounding at all.
 //   * the epilogue turns E into t = s_u E, psi = exp(-t) (or the RPLE logistic terms) in fp32, and
@@ -205,14 +205,17 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_unsign
 // fixed-point helpers
 // ------------------------------------------------------------------------------------------
 // Two precision levels of the iterate:
-//   fine   : lattice 2^-24, |x| < 8, 4 limbs (28 bits)      -- final rounds
-//   coarse : lattice 2^-20, |x| < 1, 3 limbs (21 bits)      -- while the gradient mapping is >> the lattice
-//   rough  : lattice 2^-13, |x| < 1, 2 limbs (14 bits), ONE residual digit plane (8 bits) -- the first rounds of a cold
-//            start, where the iterate moves by >> 1e-4 per round and a gradient noise of ~1e-5 is irrelevant
-constexpr double X_LATTICE_FINE = 1.0 / 16777216.0, X_LATTICE_COARSE = 1.0 / 1048576.0, X_LATTICE_ROUGH = 1.0 / 8192.0;
+//   fine   : lattice 2^-24, |x| < 7.9, 4 limbs                  -- tolerances below what the coarse lattice resolves, |x| >= 1.95
+//   coarse : lattice 2^-22, |x| < 1.95, 3 limbs (24 bits)       -- the working level: the snapped iteration stops within half a
+//            lattice unit of its fixed point, i.e. at a prox-gradient mapping of <= L * 2^-23 ~ 3e-7
+//   rough  : lattice 2^-14, |x| < 1.95, 2 limbs (16 bits), ONE residual digit plane (8 bits) -- opt-in experiment (fista.cu)
+// Digits are balanced base 256 ([-128, 127], the full int8 range; round 1 used base 128 and gave away one bit per limb:
+// its 3-limb level had lattice 2^-20 over |x| < 1, too coarse for any node to meet tol = 1e-6 on it).
+constexpr double X_LATTICE_FINE = 1.0 / 16777216.0, X_LATTICE_COARSE = 1.0 / 4194304.0, X_LATTICE_ROUGH = 1.0 / 16384.0;
 constexpr int X_LIMBS_MAX = 4;
-// representable range of the balanced base-128 limbs: 3 limbs hold |q| <= 1040000 (x 2^-20), 4 limbs |q| <= 134000000 (x 2^-24)
-constexpr double X_RANGE_COARSE = 0.99, X_RANGE_FINE = 7.9;
+// representable range of the balanced base-256 limbs: 2 limbs hold |q| <= 32000 (x 2^-14), 3 limbs |q| <= 8300000 (x 2^-22);
+// the 4-limb level keeps |q| <= 134000000 (x 2^-24: |x| < 7.99), far inside its 32 bits
+constexpr double X_RANGE_COARSE = 1.95, X_RANGE_FINE = 7.9;
 constexpr int NODE_TILE1 = 64;                   // nodes per energy tile (4 limbs -> N = 256)
 constexpr int NODE_TILE2 = 128;                  // nodes per gradient tile (M = 128)
 
@@ -224,11 +227,14 @@ __host__ __device__ constexpr int r_qmax(int nR) { return nR == 1 ? 120 : (nR ==
 __host__ __device__ constexpr unsigned r_bias(int nR) { return nR == 1 ? 0x80u : (nR == 2 ? 0x8000u : (nR == 3 ? 0x400000u : 0x80000000u)); }
 __host__ __device__ constexpr float r_magic(int nR) { return nR == 1 ? 12582912.f + 128.f : (nR == 2 ? 12582912.f + 32768.f : 12582912.f); }
 
-__device__ __forceinline__ int balanced_digit(int& q) {   // returns q mod 128 in [-64, 63], q <- (q - d) / 128
-    const int d = ((q + 64) & 127) - 64;
-    q = (q - d) >> 7;
+__device__ __forceinline__ int balanced_digit(int& q) {   // returns q mod 256 in [-128, 127], q <- (q - d) / 256
+    const int d = ((q + 128) & 255) - 128;
+    q = (q - d) >> 8;
     return d;
 }
+// Limb sums -> the integer energy, in wrap-around (unsigned) arithmetic: partial products may leave the int32 range, the
+// energy itself (|E| <= |x_u|_1 / lattice) does not.
+__device__ __forceinline__ int join2(int hi, int lo) { return (int)((unsigned)hi * 256u + (unsigned)lo); }
 
 
 // x [Nn x Fp] (double, on the lattice) -> limb tiles X [(tile*xl + limb)*node_tile + i][Fp] and per-node residual scales
@@ -241,8 +247,8 @@ __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __rest
     const int u = (slot < Nn) ? (act_idx ? act_idx[slot] : slot) : Nn;          // Nn here = number of slots in use; padding slots hold x = 0
     const bool live = slot < Nn && u >= 0;
     __shared__ double red[4];
-    // largest |q| that xl balanced base-128 digits can hold
-    const long long qcap = xl == 2 ? 8100LL : (xl == 3 ? 1040000LL : 134000000LL);
+    // largest |q| that xl balanced base-256 digits can hold (4 limbs: the |x| < 7.99 range of the fine level)
+    const long long qcap = xl == 2 ? 32000LL : (xl == 3 ? 8300000LL : 134000000LL);
     double l1 = 0.0;
     for (int f = threadIdx.x; f < Fp; f += blockDim.x) {
         const double v = live ? x[(int64_t)u * Fp + f] : 0.0;
@@ -261,6 +267,8 @@ __global__ void __launch_bounds__(128) tc_quantize_x_kernel(const double* __rest
     __syncthreads();
     if (threadIdx.x == 0) {
         const double B = red[0] + red[1] + red[2] + red[3];   // |t| <= B for every sample
+        // the 3-limb epilogue joins the limb sums in 32-bit arithmetic: |E| / lattice <= B * 2^22 must stay below 2^31
+        if (xl == 3 && B >= 500.0) atomicOr(flags, 2);
         // residual bound: RISE/logRISE  w e^{-t} <= wmax e^B;  RPLE  2 w sigma(-2t) <= 2 wmax
         const double top = (form == GML_B200_RPLE) ? 2.0 * wmax : wmax * exp(fmin(B, 80.0));
         const float inv = (float)(r_qmax(nR) / (top * 1.000001));
@@ -386,9 +394,9 @@ __device__ __forceinline__ void energy_epilogue_math(const EnergyParams& p, uint
             const uint32_t sgn = ((i & 3) == 3 ? sw[i >> 2] : (sw[i >> 2] << (24 - 8 * (i & 3)))) & 0x80000000u;
             // recombine the limb sums: exact integers, at most one rounding
             float e;
-            if (XL == 2) e = __int2float_rn(a0[i] * 128 + a1[i]);
-            else if (XL == 3) e = __int2float_rn((a0[i] * 128 + a1[i]) * 128 + a2[i]);
-            else e = fmaf(__int2float_rn(a0[i] * 128 + a1[i]), 16384.f, __int2float_rn(a2[i] * 128 + a3[i]));
+            if (XL == 2) e = __int2float_rn(join2(a0[i], a1[i]));
+            else if (XL == 3) e = __int2float_rn(join2(join2(a0[i], a1[i]), a2[i]));       // exact in fp32 while |E| < 4
+            else e = fmaf(__int2float_rn(join2(a0[i], a1[i])), 65536.f, __int2float_rn(join2(a2[i], a3[i])));
             const float es = __uint_as_float(__float_as_uint(e) ^ sgn);        // s_u * E / lattice
             float fterm, gterm;
             if (FORM == GML_B200_RPLE) {
@@ -611,9 +619,9 @@ __device__ __forceinline__ void energy_chunk_math(const EnergyParams& p, int32_t
         const uint32_t w = i < 4 ? sw0 : sw1;
         const uint32_t sb_top = (i & 3) == 3 ? w : (w << (24 - 8 * (i & 3)));      // spin byte (0x01 / 0xFF / 0x00) in the top byte
         float e;
-        if (XL == 2) e = __int2float_rn(a[0][i] * 128 + a[1][i]);
-        else if (XL == 3) e = __int2float_rn((a[0][i] * 128 + a[1][i]) * 128 + a[2][i]);
-        else e = fmaf(__int2float_rn(a[0][i] * 128 + a[1][i]), 16384.f, __int2float_rn(a[2][i] * 128 + a[3][i]));
+        if (XL == 2) e = __int2float_rn(join2(a[0][i], a[1][i]));
+        else if (XL == 3) e = __int2float_rn(join2(join2(a[0][i], a[1][i]), a[2][i]));
+        else e = fmaf(__int2float_rn(join2(a[0][i], a[1][i])), 65536.f, __int2float_rn(join2(a[2][i], a[3][i])));
         const float es = flip_sign(e, sb_top);
         float fterm, gterm;
         if (FORM == GML_B200_RPLE) {
@@ -1364,18 +1372,8 @@ struct BackendTC : EvalBackend {
         return (int)std::min<int64_t>(best, pair_blocks);
     }
 
-    // The coarse level's 3 limbs hold |q| <= 1040000 lattice units: lattice 2^-20 covers |x| < 0.99 (the default, safe for a
-    // cold start), 2^-21 covers |x| < 0.495, ...  A finer coarse lattice lets nodes meet the tolerance on the coarse level
-    // (the snapped iteration stops within half a lattice unit of its fixed point: a gradient mapping of up to L * lattice / 2).
-    double coarse_lattice = X_LATTICE_COARSE;
-    double set_coarse_range(double need) override {
-        double lat = X_LATTICE_COARSE;
-        for (int i = 0; i < 2 && X_RANGE_COARSE * (lat * 0.5 / X_LATTICE_COARSE) >= need; ++i) lat *= 0.5;
-        coarse_lattice = lat;
-        return lat;
-    }
-    double lattice() const override { return level < 0 ? X_LATTICE_ROUGH : (level == 0 ? coarse_lattice : X_LATTICE_FINE); }
-    double x_range() const override { return level < 0 ? X_RANGE_COARSE : (level == 0 ? X_RANGE_COARSE * (coarse_lattice / X_LATTICE_COARSE) : X_RANGE_FINE); }
+    double lattice() const override { return level < 0 ? X_LATTICE_ROUGH : (level == 0 ? X_LATTICE_COARSE : X_LATTICE_FINE); }
+    double x_range() const override { return level <= 0 ? X_RANGE_COARSE : X_RANGE_FINE; }
     int level_xl() const { return level < 0 ? 2 : (level == 0 ? 3 : 4); }
     int level_nr() const { return level < 0 ? 1 : (level == 0 ? std::max(2, nR - 1) : nR); }
     // rounding noise of a gradient component: ~0.29 sqrt(K) wmax e^B / qmax(nr); e^B ~ 20 as a typical upper value

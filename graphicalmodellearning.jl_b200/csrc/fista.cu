@@ -155,8 +155,9 @@ __global__ void __launch_bounds__(128) fista_accept_kernel(FistaState s) {
     }
     // Coarse level, when its gradient noise is far below the tolerance (16-bit residuals: ~6e-8 at C3): the stopping rule
     // -- prox-gradient mapping at Y <= tol -- is evaluated with the EXACT prox point; a node that meets it is done and
-    // returns that point (not its snap to the coarse lattice).  Only nodes that the 2^-20 lattice keeps above tol (their Y
-    // cannot get close enough to the fixed point) go on to the fine level.
+    // returns that point (not its snap to the coarse lattice).  Only nodes that the coarse lattice keeps above tol (the
+    // snapped iteration stops within half a lattice unit of its fixed point: a gradient mapping of up to L * 2^-23) go on to
+    // the fine level.
     if (!s.fine && s.coarse_retire && s.gtrue[u] <= s.tol && !was_clamped) {
         const double Lu = s.L[u], thr = s.lambda / Lu;
         for (int f = threadIdx.x; f < s.Fp; f += blockDim.x) {
@@ -233,14 +234,6 @@ __global__ void fista_init_kernel(FistaState s, double L0) {
     s.L[u] = L0 > 0.0 ? L0 : s.L[u] * -L0;      // first level: initial estimate; later levels: rescale by rho ratio
     s.t[u] = 1.0; s.status[u] = 0; s.gmap[u] = 1e300; s.obj[u] = 0.0;
     s.best[u] = 1e300; s.stall[u] = 0; s.streak[u] = 0; s.clamped[u] = 0;
-}
-
-// largest |x| of a start point (bits of a non-negative double order like the number)
-__global__ void fista_absmax_kernel(const double* __restrict__ x, int64_t n, unsigned long long* __restrict__ out) {
-    double m = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmax(m, fabs(x[i]));
-    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }
 
 // start point of a warm-started solve -> the lattice / range of the precision level it is first evaluated on
@@ -390,25 +383,6 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
             s.coarse_retire = (level == 0 && s.eps_g <= 0.25 * s.tol) ? 1 : 0;
         };
         sync_level();
-        // A known start point (supplied, or the mean-field start below) tells how large the coefficients are: the coarse
-        // level then takes the finest lattice whose range covers them with 8 % to spare.  Leaving the range later is
-        // caught by the quantiser (device_flags) and moves the solve to the fine level, as before.
-        auto fit_coarse_lattice = [&](const double* x) {
-            if (level != 0) return;
-            GML_CUDA(cudaMemsetAsync(gmax.p, 0, sizeof(unsigned long long), st));
-            fista_absmax_kernel<<<296, 256, 0, st>>>(x, (int64_t)nx, gmax.p);
-            GML_LAUNCHED();
-            double m = 0.0;
-            GML_CUDA(cudaMemcpyAsync(&m, gmax.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-            GML_CUDA(cudaStreamSynchronize(st));
-            if (!(m > 0.0) || !std::isfinite(m)) return;
-            const double lat = be->set_coarse_range(1.08 * m);
-            if (lat > 0.0) {
-                sync_level();
-                if (o.verbose > 0) fprintf(stderr, "[gml_b200] fista: start point max |x| = %.4g -> coarse lattice 2^%d\n", m, (int)std::lround(std::log2(lat)));
-            }
-        };
-        if (prob.x0 && li == 0) fit_coarse_lattice(r.x.p);
         if (prob.x0 && li == 0 && s.lattice > 0.0) {
             // a warm start (e.g. the previous point of a lambda path, on the fine lattice) is first evaluated on this
             // level's lattice: move X and Y there, so that the stored (f, G) belong to the point the driver holds
@@ -444,9 +418,8 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
         const bool mf_default = hist.N >= 128 && hist.N <= 2048 && (o.reserved[7] & 4) == 0;
         if (li == 0 && strides.size() == 1 && !prob.x0 && ((o.reserved[7] & 1) != 0 || mf_default) && Nn == hist.N && prob.Q == hist.base.p &&
             prob.F == hist.N + 1) {
-            const double xmax = level <= 0 ? 0.9 : 7.0;
+            const double xmax = level <= 0 ? 1.9 : 7.0;
             if (meanfield_start(G.p, Nn, Fp, prob.pen.p, xmax, s.lattice, Y.p, st)) {
-                fit_coarse_lattice(Y.p);          // (a point of the 2^-20 lattice is a point of every finer one)
                 GML_CUDA(cudaMemcpyAsync(r.x.p, Y.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
                 GML_CUDA(cudaMemcpyAsync(Z.p, Y.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
                 be->eval(Y.p, true, fY.p, G.p, st); ++n_fg; fg_units += pass_units();

@@ -10,37 +10,46 @@ from __future__ import annotations
 
 import numpy as np
 
-X_LATTICE_FINE, X_LATTICE_COARSE = 2.0 ** -24, 2.0 ** -20
+X_LATTICE_FINE, X_LATTICE_COARSE, X_LATTICE_ROUGH = 2.0 ** -24, 2.0 ** -22, 2.0 ** -14
 
 
 def r_bias(nr: int) -> int:
-    return {2: 0x8000, 3: 0x400000, 4: 0x80000000}[nr]
+    return {1: 0x80, 2: 0x8000, 3: 0x400000, 4: 0x80000000}[nr]
 
 
 def r_magic(nr: int) -> np.float32:
-    return np.float32(12582912.0 + 32768.0) if nr == 2 else np.float32(12582912.0)
+    return np.float32(12582912.0 + {1: 128.0, 2: 32768.0}.get(nr, 0.0))
 
 
 def balanced_limbs(q: np.ndarray, xl: int) -> np.ndarray:
     """q (int64, |q| within the range of xl digits) -> [xl, ...] int8 limbs, most significant first:
-    digits 1..xl-1 are balanced base-128 digits in [-64, 63], digit 0 takes what is left (tc_quantize_x_kernel)."""
+    digits 1..xl-1 are balanced base-256 digits in [-128, 127] (the full int8 range), digit 0 takes what is left
+    (tc_quantize_x_kernel)."""
     q = q.astype(np.int64).copy()
     d = np.zeros((xl,) + q.shape, dtype=np.int64)
     for j in range(xl - 1, 0, -1):
-        dj = ((q + 64) & 127) - 64
-        q = (q - dj) >> 7
+        dj = ((q + 128) & 255) - 128
+        q = (q - dj) >> 8
         d[j] = dj
     d[0] = q
-    assert np.all(np.abs(d[0]) <= 127), "iterate outside the lattice range"
+    assert np.all(d[0] <= 127) and np.all(d[0] >= -128), "iterate outside the lattice range"
     return d.astype(np.int8)
 
 
 def recombine_limb_sums(acc: np.ndarray) -> np.ndarray:
-    """[xl, ...] int32 limb sums (most significant first) -> exact integer energy in lattice units (epilogue)."""
-    e = acc[0].astype(np.int64)
-    for j in range(1, acc.shape[0]):
-        e = e * 128 + acc[j].astype(np.int64)
-    return e
+    """[xl, ...] int32 limb sums (most significant first) -> exact integer energy in lattice units (epilogue).
+    The kernel joins them in 32-bit wrap-around arithmetic (join2): partial products may leave the int32 range, the
+    energy itself does not -- restated here with explicit wrapping."""
+    def join2(hi, lo):
+        return ((hi.astype(np.int64) * 256 + lo.astype(np.int64) + 2 ** 31) % 2 ** 32) - 2 ** 31
+    xl = acc.shape[0]
+    if xl == 2:
+        return join2(acc[0], acc[1])
+    if xl == 3:
+        return join2(join2(acc[0], acc[1]), acc[2])
+    # 4 limbs: the two 16-bit halves are joined separately and combined in floating point (fmaf(hi, 65536, lo)); the
+    # integer they represent:
+    return join2(acc[0], acc[1]) * 65536 + join2(acc[2], acc[3])
 
 
 def fma_f32(a: np.ndarray, b: np.ndarray, c) -> np.ndarray:

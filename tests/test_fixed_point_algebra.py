@@ -1,6 +1,6 @@
 """CPU checks of the integer / float32 identities the tensor-core backend relies on (oracle/fixed_point.py restates
 the kernels' number representations in numpy).  They hold exactly -- no tolerances:
-  * the balanced base-128 limbs of a lattice point recombine to the point, and the limb-wise contraction equals the
+  * the balanced base-256 limbs of a lattice point recombine to the point, and the limb-wise contraction equals the
     integer contraction (energy GEMM),
   * the bytes of float_as_int(fma(g, +-scale, magic)) are the digits of round(g * +-scale) + BIAS (epilogue),
   * sum_k digits(k) S[k,f] - BIAS colsum[f] = sum_k q_k S[k,f] (gradient GEMM with unsigned digits)."""
@@ -10,7 +10,7 @@ import pytest
 import fixed_point as fx
 
 
-@pytest.mark.parametrize("xl,lattice,xmax", [(4, fx.X_LATTICE_FINE, 7.9), (3, fx.X_LATTICE_COARSE, 0.99)])
+@pytest.mark.parametrize("xl,lattice,xmax", [(4, fx.X_LATTICE_FINE, 7.9), (3, fx.X_LATTICE_COARSE, 1.95), (2, fx.X_LATTICE_ROUGH, 1.95)])
 def test_limbs_recombine_and_contract_exactly(xl, lattice, xmax):
     rng = np.random.default_rng(xl)
     F, K = 257, 96
@@ -18,15 +18,15 @@ def test_limbs_recombine_and_contract_exactly(xl, lattice, xmax):
     x[:4] = [xmax, -xmax, lattice, -lattice]
     q = np.rint(x / lattice).astype(np.int64)
     limbs = fx.balanced_limbs(q, xl)
-    assert limbs.dtype == np.int8 and np.all(limbs[1:] >= -64) and np.all(limbs[1:] <= 63)
+    assert limbs.dtype == np.int8
     assert np.array_equal(fx.recombine_limb_sums(limbs.astype(np.int32)), q)
     S = rng.choice(np.array([-1, 1], dtype=np.int8), size=(K, F))
     acc = np.stack([S.astype(np.int32) @ limbs[j].astype(np.int32) for j in range(xl)])      # what the MMAs accumulate
-    assert np.all(np.abs(acc) <= 64 * 1024 * 2)
+    assert np.all(np.abs(acc) <= 128 * F)                  # int32 accumulators: far inside their range
     assert np.array_equal(fx.recombine_limb_sums(acc), S.astype(np.int64) @ q)
 
 
-@pytest.mark.parametrize("nr,qmax", [(2, 32000), (3, 4000000)])
+@pytest.mark.parametrize("nr,qmax", [(1, 120), (2, 32000), (3, 4000000)])
 def test_residual_digits_are_bytes_of_the_rounding_word(nr, qmax):
     rng = np.random.default_rng(nr)
     n = 200_000
@@ -44,7 +44,7 @@ def test_residual_digits_are_bytes_of_the_rounding_word(nr, qmax):
     assert np.all(np.abs(got) <= qmax + 1) and digits.dtype == np.uint8
 
 
-@pytest.mark.parametrize("nr,qmax", [(2, 32000), (3, 4000000)])
+@pytest.mark.parametrize("nr,qmax", [(1, 120), (2, 32000), (3, 4000000)])
 def test_bias_is_removed_exactly_by_the_column_sums(nr, qmax):
     rng = np.random.default_rng(10 + nr)
     K, F = 4096, 33

@@ -126,7 +126,7 @@ def test_eval_rejects_points_outside_the_fixed_point_range():
     with pytest.raises(gml_b200.GMLB200Error) as e:
         sess.eval_pairwise(RISE(), x, "fista_tc")
     assert e.value.code == 1
-    x[3, 5] = 1.5
+    x[3, 5] = 2.5
     with pytest.raises(gml_b200.GMLB200Error):
         sess.eval_pairwise(RISE(), x, "fista_tc", coarse=True)
     f, _ = sess.eval_pairwise(RISE(), x, "fista_tc")                # fine level holds it
