@@ -127,7 +127,9 @@ def test_c2_active_set_compaction_changes_nothing(c2_session):
     assert ia["evals"] < 0.9 * ib["evals"]          # the compacted passes did less work
     c = sess.solve_pairwise(RISE(0.4, False), B200(compaction=True))
     d = sess.solve_pairwise(RISE(0.4, False), B200(compaction=False))
-    assert np.abs(c - d).max() <= 5e-6 and np.abs(c - a).max() <= 5e-6
+    # (two solves that each stop at a prox-gradient mapping of 1e-6 -- on different precision levels -- are each within
+    # ~tol / mu of the optimum)
+    assert np.abs(c - d).max() <= 5e-6 and np.abs(c - a).max() <= 1e-5
 
 
 def test_device_histogram_builder_and_sampler():
