@@ -249,7 +249,10 @@ void solve_pairwise_rows_one(gml_b200_handle* h, int formulation, double lambda,
     pairwise_setup_kernel<<<p.Nn, 128, 0, st>>>(N, p.Fp, nb, p.Nn, p.spin_row.p, p.pen.p);
     GML_LAUNCHED();
     SolveResult r;
-    r.want_objective = d_obj != nullptr;      // the objective at the returned point costs one more pass over the histogram
+    // The objective at the returned point costs one more pass over the histogram: only when somebody asked for it.  In a
+    // sample-sharded solve that pass contains an all-reduce, so EVERY rank must make the same choice (the callers pass the
+    // same arguments on all ranks; the single-process form hands the other devices a scratch buffer when device 0 asks).
+    r.want_objective = d_obj != nullptr;
     int solver_used = 0;
     if (warm && warm->p) p.x0 = warm->p;
     run_solver(p, o, r, solver_used, st);
@@ -982,9 +985,10 @@ static int learn_pairwise_multi_device_samples(const HostSource& src, int64_t K,
                 const double lam = src.lambda_for(lambda, N, gml_b200_num_samples(h));     // global M after the globalize step
                 if (r == 0) rc = gml_b200_solve_pairwise(h, formulation, lam, symmetrize, &o, out_theta, out_objective, &sts[r]);
                 else {
-                    DevBuf<double> rows;
-                    try { rows.alloc((size_t)N * N); } catch (const CudaError& e) { rc = e.code; }
-                    if (rc == GML_B200_OK) rc = gml_b200_solve_pairwise_device(h, formulation, lam, &o, rows.p, nullptr, &sts[r]);
+                    DevBuf<double> rows, obj_scratch;
+                    try { rows.alloc((size_t)N * N); if (out_objective) obj_scratch.alloc(N); } catch (const CudaError& e) { rc = e.code; }
+                    if (rc == GML_B200_OK)      // same passes as device 0: the objective pass is a collective
+                        rc = gml_b200_solve_pairwise_device(h, formulation, lam, &o, rows.p, out_objective ? obj_scratch.p : nullptr, &sts[r]);
                     cudaStreamSynchronize(h->own_stream);
                 }
                 sts[r].pack_ms = up.pack_ms; sts[r].h2d_ms = up.h2d_ms; sts[r].kernel_launches += up.kernel_launches;
