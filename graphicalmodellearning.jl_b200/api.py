@@ -471,7 +471,8 @@ class Session:
     def eval_pairwise(self, formulation, x: np.ndarray, backend: str = "fista_tc", want_grad: bool = True,
                       coarse: bool = False):
         """f_u and grad f_u at rows x [N x (N+1)] (couplings then field).  coarse=True evaluates on the tensor-core
-        backend's coarse precision level (iterate lattice 2^-20, |x| < 1, 16-bit residual digits)."""
+        backend's coarse precision level (iterate lattice 2^-22, |x| < 1.95, 16-bit residual digits); "rough": the opt-in
+        rough level (lattice 2^-14, one 8-bit residual plane)."""
         form_id = {RISE: 0, logRISE: 1, RPLE: 2}[type(formulation)]
         x = np.ascontiguousarray(x, dtype=np.float64)
         assert x.shape == (self.N, self.N + 1)

@@ -756,9 +756,9 @@ int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b2
         pairwise_setup_kernel<<<p.Nn, 128, 0, st>>>(N, p.Fp, nb, p.Nn, p.spin_row.p, p.pen.p);
         GML_LAUNCHED();
         std::unique_ptr<EvalBackend> be(o.solver == GML_B200_SOLVER_FISTA_TC ? make_backend_tc(p, st) : make_backend_cc(p, st));
-        if (o.reserved[5] == 1)      // evaluate on the coarse precision level (lattice 2^-20, |x| < 1)
+        if (o.reserved[5] == 1)      // evaluate on the coarse precision level (lattice 2^-22, |x| < 1.95)
             GML_REQUIRE(be->set_level(0, st), "this backend has no coarse precision level");
-        if (o.reserved[5] == 2)      // ... on the rough level (lattice 2^-13, |x| < 1, one residual digit plane)
+        if (o.reserved[5] == 2)      // ... on the rough level (lattice 2^-14, |x| < 1.95, one residual digit plane)
             GML_REQUIRE(be->set_level(-1, st), "the rough precision level is not available for this backend / histogram (it needs near-uniform counts)");
         std::vector<double> hx((size_t)p.Nn * p.Fp, 0.0);
         const double lat = be->lattice(), xmax = be->x_range();
@@ -767,7 +767,7 @@ int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b2
                 double v = (f == nb + u) ? 0.0 : x[(size_t)u * F + f];
                 GML_REQUIRE(std::isfinite(v) && (xmax <= 0.0 || std::fabs(v) <= xmax),
                             "eval: a coefficient lies outside the fixed-point range of the tensor-core backend "
-                            "(|x| < 7.9 on the fine level, < 0.99 on the coarse one); use solver = FISTA_CC");
+                            "(|x| < 7.9 on the fine level, < 1.95 on the coarse one); use solver = FISTA_CC");
                 if (lat > 0.0) v = std::nearbyint(v / lat) * lat;
                 hx[(size_t)u * p.Fp + f] = v;
             }

@@ -15,9 +15,9 @@
 //     split over sample ranges; the BIAS is removed exactly through the column sums of S (the accumulators
 //     start at -BIAS * colsum[f]); partial tiles are combined with int64 atomics, so the result is
 //     independent of the reduction order (bitwise reproducible).
-//   * two precision levels (set_level): the fine level above, and a coarse level (lattice 2^-20,
-//     3 iterate limbs, |x| < 1, one residual digit fewer) on which every node runs until it reaches the
-//     resolution of that lattice; nodes never retire on the coarse level and (f, G) are refreshed on the switch.
+//   * precision levels (set_level): the fine level above, and the coarse working level (lattice 2^-22, 3 iterate
+//     limbs, |x| < 1.95, 16-bit residuals) on which every node runs and -- at the default tolerance -- retires;
+//     an opt-in rough level (2 limbs, one residual plane) is kept as a documented negative result.
 //   * active-set compaction (set_active): the passes can be restricted to a list of nodes (slot -> node
 //     indirection in the quantiser / finaliser, spins of the listed nodes gathered into P_act).
 //

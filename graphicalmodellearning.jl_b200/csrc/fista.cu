@@ -355,10 +355,10 @@ void solve_fista_impl(const NodeProblem& prob, const gml_b200_opts& o, int backe
         GML_LAUNCHED();
         rho_prev = rho;
         GML_CUDA(cudaMemcpyAsync(Y.p, r.x.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));   // warm start
-        // Precision levels: every node first runs with a 3-limb iterate (lattice 2^-20) and one residual limb less until
-        // it reaches the tolerance or the resolution of that lattice, where it parks; when all have parked, the last
-        // rounds run at full precision.  Coarse-lattice points are fine-lattice points: the switch only refreshes (f, G).
-        // Levels of a lattice backend: 0 coarse, 1 fine; -1 rough (2-limb iterate on 2^-13, one 8-bit residual plane: 3 executed
+        // Precision levels: every node runs with a 3-limb iterate (lattice 2^-22) and 16-bit residuals; it retires there when
+        // the exact prox-gradient mapping meets the tolerance, or parks at the resolution of that lattice; when no node is
+        // active any more, the parked ones finish at full precision.  Coarse-lattice points are fine-lattice points.
+        // Levels of a lattice backend: 0 coarse, 1 fine; -1 rough (2-limb iterate on 2^-14, one 8-bit residual plane: 3 executed
         // GEMM units per pass instead of 5) only on request (opts.reserved[3] == 2).  A node runs on a level until it reaches
         // the tolerance or the resolution of that level's lattice, parks, and when all have parked the solve moves one level
         // up.  The rough level is NOT part of the default path.  Its kernels are exact for what they are given (parity-tested

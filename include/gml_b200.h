@@ -203,8 +203,8 @@ int gml_b200_threshold_device(double* d_theta, int32_t N, double tau, int64_t* o
  * the shard at a caller-supplied point.  x, g_out: (node_end-node_begin) x (N+1) row-major host arrays, feature
  * order = couplings to spins 0..N-1 (the self entry is ignored / returns 0), then the local field.  `solver`
  * selects the contraction backend (GML_B200_SOLVER_FISTA_CC or _TC; the TC backend rounds x to the lattice of the
- * precision level chosen by opts->reserved[5]: 2^-24 fine, 2^-20 coarse, 2^-13 rough; a coefficient outside the level's
- * range (|x| < 7.9 fine, < 0.99 below) is GML_B200_EINVAL, never clamped). */
+ * precision level chosen by opts->reserved[5]: 2^-24 fine, 2^-22 coarse, 2^-14 rough; a coefficient outside the level's
+ * range (|x| < 7.9 fine, < 1.95 below) is GML_B200_EINVAL, never clamped). */
 int gml_b200_eval_pairwise(gml_b200_handle* h, int32_t formulation, const gml_b200_opts* opts, const double* x,
                            double* f_out, double* g_out /* nullable */);
 

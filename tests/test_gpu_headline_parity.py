@@ -95,7 +95,7 @@ def test_rough_level_is_refused_for_strongly_weighted_histograms():
 
 @pytest.mark.parametrize("kernel", ["pair", "streaming"])
 def test_rough_level_kernels_vs_oracle(monkeypatch, kernel):
-    """The opt-in rough level (2-limb iterate on 2^-13, ONE 8-bit residual plane; needs sqrt(K) wmax <= 2e-3, i.e. >= 250 000
+    """The opt-in rough level (2-limb iterate on 2^-14, ONE 8-bit residual plane; needs sqrt(K) wmax <= 2e-3, i.e. >= 250 000
     uniformly weighted rows): exact energies, objective to fp32 accuracy, gradient to the 8-bit residual grid."""
     if kernel == "streaming":
         monkeypatch.setenv("GML_B200_NO_PAIR", "1")
