@@ -189,6 +189,22 @@ def test_fista_tc_solve_vs_oracle_n200(n200, form, creg):
     assert worst <= 1e-5 and worst_obj <= 1e-6
 
 
+@pytest.mark.parametrize("form,creg", [("RISE", 0.4), ("logRISE", 0.8), ("RPLE", 0.2)])
+def test_default_settings_solve_vs_oracle_n200(n200, form, creg):
+    """The path a plain learn(samples, formulation, B200()) takes at this size: default tol 1e-6, mean-field start,
+    retirement on the coarse level (exact prox-gradient mapping <= tol), fine level only for what is left."""
+    model, counts, spins, sess = n200
+    m = B200()
+    got, info = sess.solve_pairwise(FORMS[form](creg, False), m, return_info=True)
+    assert info["n_unconverged"] == 0 and info["solver_used"] == 3 and info["max_residual"] <= 1e-6 and info["n_stalled"] == 0
+    worst = 0.0
+    for b, e in ((0, 1), (63, 65), (199, 200)):
+        ref = c.learn_pairwise_packed(counts, spins, form, info["lambda"], False, nodes=(b, e))
+        worst = max(worst, np.abs(got[b:e] - ref[b:e]).max())
+    print(f"N=200 {form} default settings: max |dtheta| {worst:.2e}, rounds {info['iterations']}, passes {info['n_fg_passes']}")
+    assert worst <= 1e-5
+
+
 @pytest.fixture(scope="module")
 def c2():
     from test_gpu_fullsize import lattice_model
