@@ -473,8 +473,8 @@ def run_b200(args):
         e2e = {"value": float(ev2.item()) / e_med, "unit": "node*sample evals/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * n * n * world),
                "learn_seconds": e_med, "steps": len(e_times), "all_seconds": e_times,
-               "input": "pre-packed pinned host buffers: counts f64[K], spins int8 [N x K] (the reference's K x (N+1) Int64/Float64 matrix "
-                        "form is measured by scripts/bench_matrix_input.py -> profiles/)"}
+               "input": "pre-packed pinned host buffers: counts f64[K], spins int8 [N x K]; the reference's own K x (N+1) Float64 matrix "
+                        "form is e2e_from_matrix (N = 1) and scripts/bench_matrix_input.py"}
 
     # ---- parity of the timed solution: float64 KKT check of 8 random rows over the full K (CPU oracle), outside the timed region
     parity = None
@@ -486,6 +486,42 @@ def run_b200(args):
         parity = kkt_parity(rows, node_ids, np.ones(k), h_spins.numpy(), lam, mu_lower)
         parity["tolerance_note"] = ("solver stops at max-norm of the prox-gradient mapping <= tol; the KKT residual is that mapping measured with an "
                                     "independent float64 gradient over all K rows")
+
+    # ---- e2e from the reference's own input type (N = 1 only; needs ~100 GB of free host memory): learn() receives a K x (N+1)
+    # column-major Float64 matrix (src/GraphicalModelLearning.jl:69-81, test/runtests.jl:71); the call narrows it on the host
+    # cores while streaming it to the device (gml_b200_learn_pairwise_matrix), solves, symmetrises and returns the N x N matrix
+    e2e_matrix = None
+    if rank == 0 and world == 1 and not args.skip_e2e and not args.skip_matrix_e2e and h_spins is not None:
+        try:
+            import psutil
+            need = 8.0 * k * (n + 1)
+            if psutil.virtual_memory().available > need + 40e9:
+                t_build = time.time()
+                mat = np.empty((k, n + 1), dtype=np.float64, order="F")          # Julia-native layout
+                mat[:, 0] = 1.0
+                hs = h_spins.numpy()
+                for i in range(n):
+                    mat[:, 1 + i] = hs[i]
+                t_build = time.time() - t_build
+                m_times, m_ingest = [], []
+                for it in range(1 + args.matrix_e2e_steps):
+                    mm = gml_b200.B200(solver=args.solver, tol=args.tol, device=local, coarse_level=not args.no_coarse, warm_start=args.warm_start)
+                    t0 = time.perf_counter()
+                    theta = gml_b200.learn_matrix(mat, form, mm)
+                    dt = time.perf_counter() - t0
+                    if it:
+                        m_times.append(dt); m_ingest.append(mm.last_stats["h2d_ms"] * 1e-3)
+                m_med = float(np.median(m_times))
+                e2e_matrix = {"value": mm.last_stats["evals"] / m_med, "unit": "node*sample evals/s", "learn_seconds": m_med, "all_seconds": m_times,
+                              "ingest_seconds": float(np.median(m_ingest)), "matrix_bytes": int(mat.nbytes), "dtype": "float64",
+                              "max_abs_diff_vs_packed_entry": float(np.abs(theta - learned).max()), "host_matrix_build_seconds": t_build,
+                              "note": "gml_b200_learn_pairwise_matrix: threaded host narrowing (+-1 validated) overlapped with H2D of the bytes, "
+                                      "lambda and num_samples computed by the library, solve, device symmetrisation, D2H"}
+                del mat
+            else:
+                e2e_matrix = {"skipped": "less than %.0f GB of host memory available" % ((need + 40e9) / 1e9)}
+        except Exception as err:          # never lose the bench line to the optional measurement
+            e2e_matrix = {"skipped": f"{type(err).__name__}: {err}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:      # reported at N=1 only
@@ -515,7 +551,7 @@ def run_b200(args):
                 "max_abs_coupling_error_vs_truth": recon_err, "max_residual": stats["max_residual"], "n_stalled": stats.get("n_stalled", 0),
                 "support": {"mean_nnz_per_row": float(nnz_row.mean()), "max_nnz_per_row": int(nnz_row.max()), "true_degree": 4},
                 "gpu_launches": int(stats["kernel_launches"]) * args.steps,
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "multi_gpu_check": multi_gpu_check, "clocks": clocks}
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_from_matrix": e2e_matrix, "parity": parity, "multi_gpu_check": multi_gpu_check, "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -626,6 +662,8 @@ def main():
     ap.add_argument("--no-parity", dest="parity", action="store_false")
     ap.add_argument("--parity-nodes", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--skip-matrix-e2e", action="store_true")
+    ap.add_argument("--matrix-e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-rows", type=int, default=2048)
     ap.add_argument("--cpu-nodes-per-core", type=int, default=1)
     ap.add_argument("--verbose", type=int, default=0)
