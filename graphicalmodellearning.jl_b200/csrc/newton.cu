@@ -62,9 +62,7 @@ __device__ __forceinline__ double sample_value(int form, double t, double w) {
 
 // f, g, H partial sums of one (chunk, node).  NE = owned accumulator entries per thread.
 template <int NE>
-__global__ void __launch_bounds__(NT) newton_accum_kernel(NewtonParams p, int form) {
-    const int u = blockIdx.y, c = blockIdx.x;
-    if (p.conv[u]) return;
+__device__ __forceinline__ void newton_accum_body(const NewtonParams& p, int form, int u, int c) {
     const int F = p.F;
     const int P = 1 + F + F * (F + 1) / 2;
     __shared__ int8_t stat[TS][NEWTON_MAX_F];
@@ -144,6 +142,12 @@ __global__ void __launch_bounds__(NT) newton_accum_kernel(NewtonParams p, int fo
         if (e < P - 1) out[1 + e] = acc[i];
     }
 }
+template <int NE>
+__global__ void __launch_bounds__(NT) newton_accum_kernel(NewtonParams p, int form) {
+    const int u = blockIdx.y, c = blockIdx.x;
+    if (p.conv[u]) return;
+    newton_accum_body<NE>(p, form, u, c);
+}
 
 __device__ __forceinline__ double barrier_phi(double x, double lam, double mu) {
     const double eps = mu / lam, r = sqrt(eps * eps + x * x), z = eps + r;
@@ -157,10 +161,10 @@ __device__ __forceinline__ double barrier_phi(double x, double lam, double mu) {
 // mode 3: objective only (obj[u] = f + lambda*|x_pen|_1)
 constexpr int ND = 128;        // threads of the direction kernel: one per feature (F <= NEWTON_MAX_F = 128)
 static_assert(ND >= NEWTON_MAX_F, "the direction kernel initialises one feature per thread");
-__global__ void __launch_bounds__(ND) newton_direction_kernel(NewtonParams p, int form, int mode) {
-    const int u = blockIdx.x;
-    if (p.conv[u] && mode < 2) return;
+// (runs with any block size >= F: strides follow blockDim.x -- 128 threads as a kernel of its own, 256 inside the fused one)
+__device__ __forceinline__ void newton_direction_body(const NewtonParams& p, int form, int mode, int u) {
     const int F = p.F, tid = threadIdx.x;
+    const int nthr = blockDim.x;
     const int P = 1 + F + F * (F + 1) / 2;
     extern __shared__ double sm[];
     double* H = sm;                       // F x F
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(ND) newton_direction_kernel(NewtonParams p, in
     __shared__ uint8_t s_pen[NEWTON_MAX_F];
     const double lam = p.lambda;
 
-    for (int e = tid; e < P; e += ND) {
+    for (int e = tid; e < P; e += nthr) {
         double s = 0.0;
         const double* src = p.part + (int64_t)u * p.chunks * P + e;
         for (int c = 0; c < p.chunks; ++c) s += src[(int64_t)c * P];
@@ -200,11 +204,11 @@ __global__ void __launch_bounds__(ND) newton_direction_kernel(NewtonParams p, in
         __syncthreads();
         if (tid < F) g[tid] /= Z;
         __syncthreads();
-        for (int e = tid; e < F * F; e += ND) H[e] = H[e] / Z - g[e / F] * g[e % F];
+        for (int e = tid; e < F * F; e += nthr) H[e] = H[e] / Z - g[e / F] * g[e % F];
         __syncthreads();
     }
     // fixed-zero coordinates drop out of the model
-    for (int e = tid; e < F * F; e += ND) {
+    for (int e = tid; e < F * F; e += nthr) {
         const int a = e / F, b = e % F;
         if (s_pen[a] == PEN_ZERO || s_pen[b] == PEN_ZERO) H[e] = (a == b) ? 1.0 : 0.0;
     }
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(ND) newton_direction_kernel(NewtonParams p, in
         }
         __syncthreads();
         const double l = H[j * F + j];
-        for (int i = j + 1 + tid; i < F; i += ND) {
+        for (int i = j + 1 + tid; i < F; i += nthr) {
             double t = H[i * F + j];
             for (int k = 0; k < j; ++k) t -= H[i * F + k] * H[j * F + k];
             H[i * F + j] = t / l;
@@ -318,11 +322,14 @@ __global__ void __launch_bounds__(ND) newton_direction_kernel(NewtonParams p, in
     __syncthreads();
     if (tid < F) p.d[(int64_t)u * p.Fp + tid] = d[tid];
 }
+__global__ void __launch_bounds__(ND) newton_direction_kernel(NewtonParams p, int form, int mode) {
+    const int u = blockIdx.x;
+    if (p.conv[u] && mode < 2) return;
+    newton_direction_body(p, form, mode, u);
+}
 
 // smooth objective along x + alpha_i d for all alpha_i at once (energies are linear in x)
-__global__ void __launch_bounds__(NT) newton_linesearch_kernel(NewtonParams p, int form, int n_alpha) {
-    const int u = blockIdx.y, c = blockIdx.x;
-    if (p.conv[u] == 1) return;
+__device__ __forceinline__ void newton_linesearch_body(const NewtonParams& p, int form, int n_alpha, int u, int c) {
     const int F = p.F, tid = threadIdx.x;
     __shared__ double s_x[NEWTON_MAX_F], s_d[NEWTON_MAX_F];
     __shared__ double s_red[NT / 32][NALPHA];
@@ -366,12 +373,15 @@ __global__ void __launch_bounds__(NT) newton_linesearch_kernel(NewtonParams p, i
         p.part_ls[((int64_t)u * p.chunks + c) * NALPHA + tid] = s;
     }
 }
+__global__ void __launch_bounds__(NT) newton_linesearch_kernel(NewtonParams p, int form, int n_alpha) {
+    const int u = blockIdx.y, c = blockIdx.x;
+    if (p.conv[u] == 1) return;
+    newton_linesearch_body(p, form, n_alpha, u, c);
+}
 
 // one warp per node: pick the first alpha that passes Armijo, update x, flag convergence
-__global__ void newton_update_kernel(NewtonParams p, int form, int n_alpha) {
-    const int u = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (u >= p.Nn || p.conv[u] == 1) return;
+__device__ __forceinline__ void newton_update_body(const NewtonParams& p, int form, int n_alpha, int u, int lane) {
+    if (p.conv[u] == 1) return;
     const int F = p.F;
     const double lam = p.lambda;
     double* x = p.x + (int64_t)u * p.Fp;
@@ -427,6 +437,60 @@ __global__ void newton_update_kernel(NewtonParams p, int form, int n_alpha) {
     }
 }
 
+__global__ void newton_update_kernel(NewtonParams p, int form, int n_alpha) {
+    const int u = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (u >= p.Nn) return;
+    newton_update_body(p, form, n_alpha, u, threadIdx.x & 31);
+}
+
+// K5, single-launch form: for tiny problems -- a handful of nodes, a histogram of at most a few ten thousand
+// rows, <= 32 features -- the four kernels of a Newton iteration and the host read between iterations cost more than the
+// arithmetic.  One CTA per node runs the WHOLE solve: exact phase, optional barrier warm start + barrier phase, final
+// objective; the stages are the same device functions as above (one chunk = the whole histogram), separated by block
+// barriers, exchanging their partial sums through the same global scratch.  info[2u] = iterations, info[2u+1] = 1 when a
+// phase ran out of iterations.
+template <int NE>
+__global__ void __launch_bounds__(NT) newton_small_kernel(NewtonParams p, int form, int max_iter, double tol_exact, int* __restrict__ info) {
+    const int u = blockIdx.x, tid = threadIdx.x;
+    int iters = 0, unconv = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 1) {
+            if (!(p.mu > 0.0 && p.lambda > 0.0)) break;
+            // exact zeros -> their first-order barrier value (direction mode 2), then damped Newton on f + sum phi_mu
+            if (tid == 0) p.conv[u] = 0;
+            __syncthreads();
+            newton_accum_body<NE>(p, form, u, 0);
+            __syncthreads();
+            newton_direction_body(p, form, 2, u);
+            __syncthreads();
+        }
+        p.barrier = phase;
+        p.tol = phase ? 1e-15 : tol_exact;
+        int it = 0;
+        for (; it < max_iter; ++it) {
+            newton_accum_body<NE>(p, form, u, 0);
+            __syncthreads();
+            newton_direction_body(p, form, phase, u);
+            __syncthreads();
+            newton_linesearch_body(p, form, NALPHA, u, 0);
+            __syncthreads();
+            if (tid < 32) newton_update_body(p, form, NALPHA, u, tid);
+            __syncthreads();
+            if (p.conv[u] == 1) { ++it; break; }
+        }
+        iters += it;
+        if (p.conv[u] != 1) unconv = 1;
+        __syncthreads();
+    }
+    // objective at the returned point
+    if (tid == 0) p.conv[u] = 0;
+    __syncthreads();
+    newton_accum_body<NE>(p, form, u, 0);
+    __syncthreads();
+    newton_direction_body(p, form, 3, u);
+    if (tid == 0) { info[2 * u] = iters; info[2 * u + 1] = unconv; }
+}
+
 void launch_accum(const NewtonParams& P, int form, cudaStream_t st) {
     const int Ptot = P.F + P.F * (P.F + 1) / 2;
     const int ne = (int)ceil_div(Ptot, NT);
@@ -448,9 +512,12 @@ void solve_newton(const NodeProblem& prob, const gml_b200_opts& o, SolveResult& 
     const int F = prob.F, Fp = prob.Fp, Nn = prob.Nn;
     GML_REQUIRE(F <= NEWTON_MAX_F, "Newton solver supports at most 128 features per node");
     const int Ptot = 1 + F + F * (F + 1) / 2;
+    // tiny problems: the whole solve in ONE launch, one CTA per node (newton_small_kernel)
+    const bool fused = F <= 32 && h.Kp <= 32768 && !std::getenv("GML_B200_NO_FUSED_NEWTON");
     int64_t chunks = ceil_div(h.Kp, 1024);
     chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, 1184 / Nn));
     chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, (int64_t)(1 << 24) / ((int64_t)Nn * Ptot)));
+    if (fused) chunks = 1;
     const int64_t chunk_len = round_up(ceil_div(h.Kp, chunks), TS);
     chunks = ceil_div(h.Kp, chunk_len);
 
@@ -503,6 +570,26 @@ void solve_newton(const NodeProblem& prob, const gml_b200_opts& o, SolveResult& 
         GML_CUDA(cudaFuncSetAttribute(newton_direction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dir_smem));
 
     const double tol_exact = o.tol > 0 ? o.tol : 1e-12;
+    if (fused) {
+        DevBuf<int> info;
+        info.alloc((size_t)2 * Nn);
+        const int ne = (int)ceil_div(Ptot - 1, NT);
+        if (ne <= 1) newton_small_kernel<1><<<Nn, NT, dir_smem, st>>>(P, form, max_iter, tol_exact, info.p);
+        else if (ne <= 2) newton_small_kernel<2><<<Nn, NT, dir_smem, st>>>(P, form, max_iter, tol_exact, info.p);
+        else newton_small_kernel<3><<<Nn, NT, dir_smem, st>>>(P, form, max_iter, tol_exact, info.p);
+        GML_LAUNCHED();
+        std::vector<int> hinfo((size_t)2 * Nn);
+        std::vector<double> hres(Nn);
+        GML_CUDA(cudaMemcpyAsync(hinfo.data(), info.p, sizeof(int) * 2 * Nn, cudaMemcpyDeviceToHost, st));
+        GML_CUDA(cudaMemcpyAsync(hres.data(), resid.p, sizeof(double) * Nn, cudaMemcpyDeviceToHost, st));
+        GML_CUDA(cudaStreamSynchronize(st));
+        int unconv = 0, iters = 0;
+        double mr = 0.0;
+        for (int u = 0; u < Nn; ++u) { iters = std::max(iters, hinfo[2 * u]); unconv += hinfo[2 * u + 1]; mr = std::max(mr, hres[u]); }
+        const bool two_phase = o.barrier_mu > 0.0 && prob.lambda > 0.0;
+        r.iterations = iters; r.n_fg = iters + (two_phase ? 2 : 1); r.n_f = iters; r.n_unconverged = unconv; r.max_residual = mr;
+        return;
+    }
     run_phase(0, tol_exact);
     int unconverged = active;
     if (o.barrier_mu > 0.0 && prob.lambda > 0.0) {
