@@ -443,9 +443,9 @@ __global__ void newton_update_kernel(NewtonParams p, int form, int n_alpha) {
     newton_update_body(p, form, n_alpha, u, threadIdx.x & 31);
 }
 
-// K5, single-launch form: for tiny problems -- a handful of nodes, a histogram of at most a few ten thousand
-// rows, <= 32 features -- the four kernels of a Newton iteration and the host read between iterations cost more than the
-// arithmetic.  One CTA per node runs the WHOLE solve: exact phase, optional barrier warm start + barrier phase, final
+// K5, single-launch form: for tiny problems -- a handful of nodes, a histogram of at most 2048 rows (the
+// README example, the reference's test fixtures), <= 32 features -- the four kernels of a Newton iteration and the host
+// read between iterations cost more than the arithmetic.  One CTA per node runs the WHOLE solve: exact phase, optional barrier warm start + barrier phase, final
 // objective; the stages are the same device functions as above (one chunk = the whole histogram), separated by block
 // barriers, exchanging their partial sums through the same global scratch.  info[2u] = iterations, info[2u+1] = 1 when a
 // phase ran out of iterations.
@@ -512,8 +512,10 @@ void solve_newton(const NodeProblem& prob, const gml_b200_opts& o, SolveResult& 
     const int F = prob.F, Fp = prob.Fp, Nn = prob.Nn;
     GML_REQUIRE(F <= NEWTON_MAX_F, "Newton solver supports at most 128 features per node");
     const int Ptot = 1 + F + F * (F + 1) / 2;
-    // tiny problems: the whole solve in ONE launch, one CTA per node (newton_small_kernel)
-    const bool fused = F <= 32 && h.Kp <= 32768 && !std::getenv("GML_B200_NO_FUSED_NEWTON");
+    // tiny problems: the whole solve in ONE launch, one CTA per node (newton_small_kernel).  Measured: C0 (K = 8) 0.41 -> 0.29 ms
+    // per learn(); at C1 size (K = 18 700) one CTA per node sweeping the histogram alone is 5x SLOWER than the chunked
+    // kernels (9.7 against 1.9 ms), hence the small row limit.
+    const bool fused = F <= 32 && h.Kp <= 2048 && !std::getenv("GML_B200_NO_FUSED_NEWTON");
     int64_t chunks = ceil_div(h.Kp, 1024);
     chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, 1184 / Nn));
     chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, (int64_t)(1 << 24) / ((int64_t)Nn * Ptot)));
