@@ -73,7 +73,8 @@ typedef struct gml_b200_opts {
                             reserved[6] != 0: disable the active-set compaction of the FISTA passes;
                             reserved[7]: bit 0 force the mean-field warm start of cold full pairwise FISTA solves (default: on
                             for 128 <= N <= 2048), bit 2 switch it off, bit 1 finish every node with fp64 Newton on its
-                            identified support (exact L1 minimiser to ~1e-10 for any number of features) */
+                            identified support (exact L1 minimiser to ~1e-10 for any number of features; a node whose support
+                            exceeds 128 coordinates keeps its first-order solution -- reported with verbose > 0) */
 } gml_b200_opts;
 
 typedef struct gml_b200_stats {
