@@ -7,8 +7,8 @@
 // optimum instead of |x| ~ 0.4 (float64 emulation of the driver: ~30 % fewer rounds, scripts/dev_warmstart_study.py).
 // The problem is convex, so the start changes the path, not the answer (src/GraphicalModelLearning.jl:169-177).
 //
-// Everything runs on the device: N x N Gauss-Jordan inversion of the (ridge-stabilised) connected correlation matrix,
-// one launch per pivot over a ping-pong pair of matrices (symmetric positive definite: no pivoting needed).
+// Everything runs on the device: blocked N x N Gauss-Jordan inversion of the (ridge-stabilised) connected correlation
+// matrix over a ping-pong pair of matrices (symmetric positive definite: no pivoting needed).
 #include "common.cuh"
 
 #include <cmath>
@@ -27,21 +27,60 @@ __global__ void mf_build_kernel(const double* __restrict__ G0, int N, int Fp, do
     A[idx] = c - mi * mj + (i == j ? ridge : 0.0);
 }
 
-// one Gauss-Jordan step on pivot p, out of place: after N steps the output holds the inverse
-__global__ void mf_gauss_jordan_kernel(const double* __restrict__ Ain, double* __restrict__ Aout, int N, int p, int* __restrict__ bad) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)N * N) return;
-    const int i = (int)(idx / N), j = (int)(idx % N);
-    const double piv = Ain[(int64_t)p * N + p];
-    if (!(piv > 1e-12) || !isfinite(piv)) { if (idx == 0) *bad = 1; Aout[idx] = Ain[idx]; return; }
-    const double rp = 1.0 / piv;
-    double out;
-    if (i == p) out = (j == p) ? rp : Ain[(int64_t)p * N + j] * rp;
-    else {
-        const double f = Ain[(int64_t)i * N + p];
-        out = (j == p) ? -f * rp : Ain[idx] - f * Ain[(int64_t)p * N + j] * rp;
+// Blocked Gauss-Jordan inversion, out of place over a ping-pong pair, MF_B pivots per step (symmetric positive definite +
+// ridge: no pivoting needed).  With K = the MF_B rows / columns of the step, D = A[K,K]:
+//     out[K,K]   = D^-1                         out[K,j]   = D^-1 A[K,j]                  (j not in K)
+//     out[i,K]   = -A[i,K] D^-1                 out[i,j]   = A[i,j] - A[i,K] D^-1 A[K,j]  (i, j not in K)
+// i.e. MF_B steps of the scalar elimination at once: ~3 N / MF_B launches instead of N (the scalar form, one launch per
+// pivot, was 8.5 ms of every C3 solve -- and, not being divided by the GPU count, most of what separated the 8-GPU run from
+// perfect scaling).
+constexpr int MF_B = 32;
+
+// D^-1 of the diagonal block (one CTA, scalar Gauss-Jordan in shared memory); rows / columns beyond N act as identity
+__global__ void __launch_bounds__(MF_B * MF_B) mf_block_inverse_kernel(const double* __restrict__ A, int N, int k0, double* __restrict__ Dinv,
+                                                                     int* __restrict__ bad) {
+    __shared__ double S[MF_B][MF_B + 1];
+    const int r = threadIdx.x / MF_B, c = threadIdx.x % MF_B;
+    const int gr = k0 + r, gc = k0 + c;
+    S[r][c] = (gr < N && gc < N) ? A[(int64_t)gr * N + gc] : (r == c ? 1.0 : 0.0);
+    __syncthreads();
+    for (int p = 0; p < MF_B; ++p) {
+        const double piv = S[p][p], f = S[r][p], prow = S[p][c], v = S[r][c];
+        __syncthreads();
+        if (!(piv > 1e-12) || !isfinite(piv)) { if (threadIdx.x == 0) *bad = 1; }
+        else {
+            const double rp = 1.0 / piv;
+            S[r][c] = (r == p) ? (c == p ? rp : prow * rp) : (c == p ? -f * rp : v - f * prow * rp);
+        }
+        __syncthreads();
     }
-    Aout[idx] = out;
+    Dinv[r * MF_B + c] = S[r][c];
+}
+
+// T[r, j] = sum_c D^-1[r, c] A[k0 + c, j]   (MF_B x N row panel)
+__global__ void mf_row_panel_kernel(const double* __restrict__ A, int N, int k0, const double* __restrict__ Dinv, double* __restrict__ T) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (j >= N) return;
+    double acc = 0.0;
+    for (int c = 0; c < MF_B && k0 + c < N; ++c) acc += Dinv[r * MF_B + c] * A[(int64_t)(k0 + c) * N + j];
+    T[(int64_t)r * N + j] = acc;
+}
+
+__global__ void mf_block_update_kernel(const double* __restrict__ Ain, double* __restrict__ Aout, int N, int k0, const double* __restrict__ Dinv,
+                                       const double* __restrict__ T) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= N) return;
+    const bool iK = i >= k0 && i < k0 + MF_B, jK = j >= k0 && j < k0 + MF_B;
+    double out;
+    if (iK && jK) out = Dinv[(i - k0) * MF_B + (j - k0)];
+    else if (iK) out = T[(int64_t)(i - k0) * N + j];
+    else {
+        const double* arow = Ain + (int64_t)i * N + k0;
+        double acc = 0.0;
+        if (jK) { for (int c = 0; c < MF_B && k0 + c < N; ++c) acc += arow[c] * Dinv[c * MF_B + (j - k0)]; out = -acc; }
+        else { for (int c = 0; c < MF_B && k0 + c < N; ++c) acc += arow[c] * T[(int64_t)c * N + j]; out = Ain[(int64_t)i * N + j] - acc; }
+    }
+    Aout[(int64_t)i * N + j] = out;
 }
 
 // x0[u, j] = -Ainv[u, j] (couplings), x0[u, N] = atanh(m_u) - sum_j J_uj m_j (field); clamped, snapped to the lattice,
@@ -88,9 +127,15 @@ bool meanfield_start(const double* G0, int N, int Fp, const uint8_t* pen, double
     const unsigned grid = (unsigned)ceil_div(nn, 256);
     mf_build_kernel<<<grid, 256, 0, st>>>(G0, N, Fp, 1e-6, A.p);
     GML_LAUNCHED();
+    DevBuf<double> Dinv, T;
+    Dinv.alloc(MF_B * MF_B); T.alloc((size_t)MF_B * N);
     double *in = A.p, *out = B.p;
-    for (int p = 0; p < N; ++p) {
-        mf_gauss_jordan_kernel<<<grid, 256, 0, st>>>(in, out, N, p, bad.p);
+    for (int k0 = 0; k0 < N; k0 += MF_B) {
+        mf_block_inverse_kernel<<<1, MF_B * MF_B, 0, st>>>(in, N, k0, Dinv.p, bad.p);
+        GML_LAUNCHED();
+        mf_row_panel_kernel<<<dim3((unsigned)ceil_div(N, 256), MF_B), 256, 0, st>>>(in, N, k0, Dinv.p, T.p);
+        GML_LAUNCHED();
+        mf_block_update_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)N), 256, 0, st>>>(in, out, N, k0, Dinv.p, T.p);
         GML_LAUNCHED();
         std::swap(in, out);
     }
