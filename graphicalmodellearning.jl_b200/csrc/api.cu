@@ -391,7 +391,7 @@ MultibodyLayout multibody_layout(int N, int order) {
 
 extern "C" {
 
-const char* gml_b200_version(void) { return "gml_b200 0.1.0 (sm_100a)"; }
+const char* gml_b200_version(void) { return "gml_b200 0.2.0 (sm_100a)"; }
 const char* gml_b200_last_error(void) { return g_error.c_str(); }
 
 int gml_b200_device_count(void) {
